@@ -1,0 +1,1256 @@
+// Hand-written sm_100a kernels of the square-root BA inner loop.  See DESIGN.md for the data layout,
+// the algorithmic bytes of every kernel and the reference function each one replaces.
+// "ref:" citations are relative to /root/reference/src/rootba/.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+
+#include "layout.hpp"
+
+namespace rba {
+
+// ------------------------------------------------------------------------------------------------
+// scalar traits
+// ------------------------------------------------------------------------------------------------
+template <class S> struct ST;
+template <> struct ST<float> {
+  using V2 = float2;
+  using V4 = float4;
+  __host__ __device__ static float eps_sqrt() { return 0.0031622776601683794f; }  // sqrt(1e-5), Sophus (A10)
+  __host__ __device__ static float eps() { return 1e-5f; }
+  __host__ __device__ static float tiny() { return FLT_MIN; }
+};
+template <> struct ST<double> {
+  using V2 = double2;
+  using V4 = double4;
+  __host__ __device__ static double eps_sqrt() { return 1e-5; }
+  __host__ __device__ static double eps() { return 1e-10; }
+  __host__ __device__ static double tiny() { return DBL_MIN; }
+};
+
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+
+struct KOpts {
+  int use_valid_projections_only;
+  int robust_norm;
+  double huber;
+  double jacobi_eps;  // effective epsilon (already resolved)
+};
+
+// PCG scalars live on the device in double (ref: cg/conjugate_gradient.hpp:124-263 keeps them in double)
+struct PcgState {
+  double rho[2];
+  double q0[2];
+  double norm_b;
+  double last_pq, last_alpha, last_zeta;
+  int iter;
+  int done;
+  int term;    // 0 NO_CONVERGENCE, 1 SUCCESS, 2 FAILURE
+  int reason;  // 0 max-iter, 1 zeta, 2 |b|=0, 3 rho, 4 beta, 5 indefinite pq, 6 alpha
+};
+
+constexpr int NPART = 64;  // blocks (= partial slots) of every vector kernel
+
+template <class S>
+struct DevPtrs {
+  // state
+  S* cams; S* lms;
+  // topology
+  const TileInfo* tiles; int ntiles;
+  const int* sorted_lm;
+  const int* slot_cam; const int* slot_lm; const S* slot_xy; int nslots;
+  // linearization storage
+  S* panel;      // Q2^T Jp panels, tile layout
+  S* rec;        // [nslots][48] = [jp(2x9) scaled | q1d(3x9) | pad 3]
+  S* q1u;        // [nslots][27] undamped Q1^T Jp
+  S* jl;         // [nslots][6]  scaled Jl (2x3)
+  S* res;        // [nslots][2]  weighted residual
+  S* lmk;        // [nsorted][24] Ru(6) q1r_u(3) Rd(6) q1r_d(3) Jl_col_scale(3) pad
+  // camera vectors [9 nc]
+  S* diag2; S* scaling; S* b; S* x; S* r; S* z; S* p; S* q; S* y; S* inc;
+  S* blocks;     // [nc][81] preconditioner blocks (damping added)
+  S* jblocks;    // [nc][81] JACOBI blocks (scaled, no damping)
+  S* inv;        // [nc][81] explicit inverses
+  // scatter buffers
+  S* yobs;       // [nyslots][9]
+  S* partial;    // [max items][9]
+  S* pblk;       // [csr_obs items][48] partial preconditioner blocks (45 used)
+  int nc;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device math (same formulas and operation order as the oracle / reference)
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__device__ __forceinline__ void quat_to_rot(const S* q, S* R) {  // Eigen::Quaternion::toRotationMatrix
+  const S x = q[0], y = q[1], z = q[2], w = q[3];
+  const S tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const S twx = tx * w, twy = ty * w, twz = tz * w;
+  const S txx = tx * x, txy = ty * x, txz = tz * x;
+  const S tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// ref: bal/bal_bundle_adjustment_helper.cpp:112-149 (linearize_point) + basalt BalCamera::project (A9)
+// JAC=false: residual only.  Jp 2x9 (pose 6 + intrinsics 3) row-major, Jl 2x3.
+template <class S, bool JAC>
+__device__ __forceinline__ bool linearize_point(const S* obs, const S* pw, const S* cam, S* res, S* Jp9, S* Jl) {
+  S R[9];
+  quat_to_rot(cam, R);
+  S pc[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) pc[r] = R[3 * r] * pw[0] + R[3 * r + 1] * pw[1] + R[3 * r + 2] * pw[2] + cam[4 + r];
+  const S f = cam[7], k1 = cam[8], k2 = cam[9];
+  const S z = pc[2];
+  const S mx = pc[0] / z, my = pc[1] / z;
+  const S mx2 = mx * mx, my2 = my * my;
+  const S r2 = mx2 + my2;
+  const S r4 = r2 * r2;
+  const S rp = S(1) + k1 * r2 + k2 * r4;
+  res[0] = f * mx * rp - obs[0];
+  res[1] = f * my * rp - obs[1];
+  if (JAC) {
+    const S tmp = k1 + k2 * S(2) * r2;
+    S d[6];
+    d[0] = f * (rp + S(2) * mx2 * tmp) / z;
+    d[4] = f * (rp + S(2) * my2 * tmp) / z;
+    d[1] = d[3] = S(2) * f * mx * my * tmp / z;
+    d[2] = -f * mx * (rp + S(2) * tmp * r2) / z;
+    d[5] = -f * my * (rp + S(2) * tmp * r2) / z;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const S d0 = d[3 * r], d1 = d[3 * r + 1], d2 = d[3 * r + 2];
+      Jp9[9 * r + 0] = d0; Jp9[9 * r + 1] = d1; Jp9[9 * r + 2] = d2;
+      Jp9[9 * r + 3] = -d1 * pc[2] + d2 * pc[1];
+      Jp9[9 * r + 4] = d0 * pc[2] - d2 * pc[0];
+      Jp9[9 * r + 5] = -d0 * pc[1] + d1 * pc[0];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Jl[3 * r + c] = d0 * R[c] + d1 * R[3 + c] + d2 * R[6 + c];
+    }
+    Jp9[6] = mx * rp; Jp9[7] = f * mx * r2; Jp9[8] = f * mx * r4;
+    Jp9[15] = my * rp; Jp9[16] = f * my * r2; Jp9[17] = f * my * r4;
+  }
+  return z >= ST<S>::eps_sqrt();
+}
+
+// ref: bal/bal_bundle_adjustment_helper.cpp:43-66
+template <class S>
+__device__ __forceinline__ void error_weight(const KOpts& o, S rsq, S& err, S& w) {
+  if (o.robust_norm == 1) {
+    const S th = (S)o.huber;
+    const S hw = rsq < th * th ? S(1) : th / sqrt(rsq);
+    err = S(0.5) * (S(2) - hw) * hw * rsq;
+    w = hw;
+  } else {
+    err = S(0.5) * rsq;
+    w = S(1);
+  }
+}
+
+template <class T>
+__device__ __forceinline__ T group_sum(T v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ bool finite_s(float v) { return isfinite(v); }
+__device__ __forceinline__ bool finite_s(double v) { return isfinite(v); }
+
+// block-wide sum of K doubles per thread -> out[blockIdx.x*K + k] (thread 0); blockDim multiple of 32, <= 1024
+template <int K>
+__device__ __forceinline__ void block_sum_store(double (&v)[K], double* out) {
+  __shared__ double sm[32][K];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < K; ++k) sm[w][k] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double s = 0;
+      for (int i = 0; i < nw; ++i) s += sm[i][k];
+      out[blockIdx.x * K + k] = s;
+    }
+  }
+  __syncthreads();
+}
+
+// sum of n <= 1024 partial doubles in a fixed order, result broadcast to every thread of the block
+__device__ __forceinline__ double block_sum_partials(const double* part, int n, int stride, int off) {
+  __shared__ double bs_sm[32];
+  __shared__ double bs_total;
+  double v = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += part[i * stride + off];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) bs_sm[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < nw; ++i) s += bs_sm[i];
+    bs_total = s;
+  }
+  __syncthreads();
+  const double r = bs_total;
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0  error  (ref: bal/bal_bundle_adjustment_helper.cpp:68-109, residual_info.cpp:97-110)
+//     thread per observation slot; accumulation in double; out partials [gridDim][6]
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(256) k_error(DevPtrs<S> D, KOpts o, double* partials, int* bad_flag) {
+  double acc[6] = {0, 0, 0, 0, 0, 0};  // all: n, err, res ; valid: n, err, res
+  bool bad = false;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < D.nslots; s += gridDim.x * blockDim.x) {
+    const int lm = D.slot_lm[s];
+    if (lm < 0) continue;
+    S obs[2] = {D.slot_xy[2 * s], D.slot_xy[2 * s + 1]};
+    S pw[3] = {D.lms[3 * lm], D.lms[3 * lm + 1], D.lms[3 * lm + 2]};
+    S cam[10];
+    const S* cp = D.cams + 10 * (size_t)D.slot_cam[s];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) cam[k] = cp[k];
+    S res[2];
+    const bool pv = linearize_point<S, false>(obs, pw, cam, res, nullptr, nullptr);
+    if (!(finite_s(res[0]) && finite_s(res[1]))) bad = true;
+    const S rsq = res[0] * res[0] + res[1] * res[1];
+    S err, w;
+    error_weight(o, rsq, err, w);
+    const double rn = (double)sqrt(rsq);
+    acc[0] += 1.0; acc[1] += (double)err; acc[2] += rn;
+    // ref: with the validity check enabled linearize_point returns false for invalid projections and they
+    // count only in "all"; with it disabled the return value is still the projection validity.
+    if (pv) { acc[3] += 1.0; acc[4] += (double)err; acc[5] += rn; }
+  }
+  if (bad) atomicOr(bad_flag, 1);
+  block_sum_store<6>(acc, partials);
+}
+
+// sums [n][K] double partials -> out[K]   (single block)
+template <int K>
+__global__ void k_sum_partials(const double* part, int n, double* out) {
+  for (int k = 0; k < K; ++k) {
+    const double s = block_sum_partials(part, n, K, k);
+    if (threadIdx.x == 0) out[k] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a  squared column norms of sqrt(w) * Jp per observation  (ref: qr/impl/landmark_block_base.ipp:493-518)
+//      thread per slot -> yobs[slot][9]; reduced per camera by k_cam_reduce (deterministic)
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(256) k_jp_norms(DevPtrs<S> D, KOpts o, int* bad_flag) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < D.nslots; s += gridDim.x * blockDim.x) {
+    const int lm = D.slot_lm[s];
+    if (lm < 0) continue;
+    S obs[2] = {D.slot_xy[2 * s], D.slot_xy[2 * s + 1]};
+    S pw[3] = {D.lms[3 * lm], D.lms[3 * lm + 1], D.lms[3 * lm + 2]};
+    S cam[10];
+    const S* cp = D.cams + 10 * (size_t)D.slot_cam[s];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) cam[k] = cp[k];
+    S res[2], Jp[18], Jl[6];
+    const bool valid = linearize_point<S, true>(obs, pw, cam, res, Jp, Jl);
+    S out[9];
+    if (!o.use_valid_projections_only || valid) {
+      bool fin = finite_s(res[0]) && finite_s(res[1]);
+#pragma unroll
+      for (int k = 0; k < 18; ++k) fin = fin && finite_s(Jp[k]);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) fin = fin && finite_s(Jl[k]);
+      if (!fin) atomicOr(bad_flag, 1);
+      S err, w;
+      error_weight(o, res[0] * res[0] + res[1] * res[1], err, w);
+      const S sw = sqrt(w);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const S a = sw * Jp[c], b = sw * Jp[9 + c];
+        out[c] = a * a + b * b;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) out[c] = 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) D.yobs[9 * (size_t)s + c] = out[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic scatter, phase 2: per-camera segmented sum of 9-vectors
+//   warp per ReduceItem (segment of a camera's slot list) -> partial[item][9]
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, const int* __restrict__ slots,
+                                                     const ReduceItem* __restrict__ items, int nitems,
+                                                     S* __restrict__ partial, const int* done) {
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb) {
+    const ReduceItem I = items[it];
+    S acc[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc[c] = 0;
+    for (int e = I.begin + lane; e < I.end; e += 32) {
+      const S* v = src + 9 * (size_t)slots[e];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) acc[c] += v[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane < 9) {
+      S v = acc[0];
+#pragma unroll
+      for (int c = 1; c < 9; ++c) if (lane == c) v = acc[c];
+      partial[9 * (size_t)it + lane] = v;
+    }
+  }
+}
+
+// out[cam*9+c] = sum over the camera's items (fixed order)
+template <class S>
+__global__ void k_cam_final(const S* __restrict__ partial, const int* __restrict__ cam_item_ptr, int nc,
+                            S* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * nc) return;
+  const int cam = i / 9, c = i - 9 * cam;
+  S s = 0;
+  for (int it = cam_item_ptr[cam]; it < cam_item_ptr[cam + 1]; ++it) s += partial[9 * (size_t)it + c];
+  out[i] = s;
+}
+
+// ref: solver/linearizor_qr.cpp:130-132
+template <class S>
+__global__ void k_scaling(const S* diag2, S* scaling, int n, S eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scaling[i] = S(1) / (eps + sqrt(diag2[i]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b  linearize + Jl scaling + Householder QR of the 3 landmark columns + write marginalised panel
+//   ref: ipp:88-147 (linearize_landmark), :571-587 (scale_Jl_cols), :717-743 (perform_qr_householder),
+//        Eigen makeHouseholder/applyHouseholderOnTheLeft, pose-Jacobian scaling ipp:589-614
+//        folded in (the scaling vector is known before this kernel runs).
+//   One warp per tile; group of G lanes per landmark.  The three reflectors are generated exactly like
+//   Eigen does on the 2n x 4 matrix [Jl | r] (shuffle reductions inside the group) and applied to the
+//   block-diagonal Jp through their compact-WY form, one output element = 3 FMAs, written straight into
+//   the coalesced panel layout.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, int scratch_per_warp, int* bad_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using V2 = typename ST<S>::V2;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  S* ws = reinterpret_cast<S*>(smem_raw) + (size_t)wib * scratch_per_warp;
+  const S eps = (S)o.jacobi_eps;
+  for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+    const TileInfo T = D.tiles[t];
+    const int n = T.n, G = T.G, KP = T.KP;
+    const int g = lane / G, j = lane - g * G;
+    const bool active = g < T.nvalid;
+    S* sJ = ws + (size_t)g * 32 * n;  // [n][26]: jp row0 (9) | jp row1 (9) | jl row0 (3) | jl row1 (3) | r (2)
+    S* sV = sJ + 26 * n;              // [2n][3] Householder vectors
+    const int slot0 = T.slot_base + g * n;
+    const int sidx = T.lm_base + g;
+    S pw[3] = {0, 0, 0};
+    if (active) {
+      const int lm = D.sorted_lm[sidx];
+      pw[0] = D.lms[3 * lm]; pw[1] = D.lms[3 * lm + 1]; pw[2] = D.lms[3 * lm + 2];
+    }
+    __syncwarp();
+    // ---- a. Jacobians of the observations (ref: ipp:106-140) ----
+    for (int i = j; i < n; i += G) {
+      S* e = sJ + 26 * i;
+      bool wrote = false;
+      if (active) {
+        const int s = slot0 + i;
+        const int cam_i = D.slot_cam[s];
+        S obs[2] = {D.slot_xy[2 * s], D.slot_xy[2 * s + 1]};
+        S cam[10];
+        const S* cp = D.cams + 10 * (size_t)cam_i;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) cam[k] = cp[k];
+        S res[2], Jp[18], Jl[6];
+        const bool valid = linearize_point<S, true>(obs, pw, cam, res, Jp, Jl);
+        if (!o.use_valid_projections_only || valid) {
+          bool fin = finite_s(res[0]) && finite_s(res[1]);
+#pragma unroll
+          for (int k = 0; k < 18; ++k) fin = fin && finite_s(Jp[k]);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) fin = fin && finite_s(Jl[k]);
+          if (!fin) atomicOr(bad_flag, 1);
+          S err, w;
+          error_weight(o, res[0] * res[0] + res[1] * res[1], err, w);
+          const S sw = sqrt(w);
+          const S* sc = D.scaling + 9 * (size_t)cam_i;
+#pragma unroll
+          for (int c = 0; c < 9; ++c) {
+            const S d = sc[c];
+            e[c] = (sw * Jp[c]) * d;
+            e[9 + c] = (sw * Jp[9 + c]) * d;
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) e[18 + c] = sw * Jl[c];
+          e[24] = sw * res[0];
+          e[25] = sw * res[1];
+          wrote = true;
+        }
+      }
+      if (!wrote)
+#pragma unroll
+        for (int c = 0; c < 26; ++c) e[c] = 0;
+    }
+    __syncwarp();
+    // ---- b. scale_Jl_cols (ref: ipp:571-587) ----
+    S cs[3] = {0, 0, 0};
+    for (int i = j; i < n; i += G) {
+      const S* e = sJ + 26 * i + 18;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) cs[c] += e[c] * e[c] + e[3 + c] * e[3 + c];
+    }
+    S jls[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      cs[c] = group_sum(cs[c], G);
+      jls[c] = S(1) / (eps + sqrt(cs[c]));
+    }
+    for (int i = j; i < n; i += G) {
+      S* e = sJ + 26 * i + 18;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { e[c] *= jls[c]; e[3 + c] *= jls[c]; }
+    }
+    __syncwarp();
+    // ---- write the per-observation records (scaled Jp, scaled Jl, weighted residual) ----
+    if (active) {
+      for (int i = j; i < n; i += G) {
+        const S* e = sJ + 26 * i;
+        S* rc = D.rec + 48 * (size_t)(slot0 + i);
+#pragma unroll
+        for (int c = 0; c < 18; ++c) rc[c] = e[c];
+        S* jo = D.jl + 6 * (size_t)(slot0 + i);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) jo[c] = e[18 + c];
+        D.res[2 * (size_t)(slot0 + i)] = e[24];
+        D.res[2 * (size_t)(slot0 + i) + 1] = e[25];
+      }
+    }
+    // ---- c. Householder QR of A = [Jl | r] (2n x 4), rows rho = 2i + parity ----
+#define A_AT(rho, c) sJ[26 * ((rho) >> 1) + ((c) < 3 ? 18 + 3 * ((rho)&1) + (c) : 24 + ((rho)&1))]
+    S tau[3];
+    const int nrows = 2 * n;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+      S ts = 0;
+      for (int rho = j; rho < nrows; rho += G)
+        if (rho > k) { const S v = A_AT(rho, k); ts += v * v; }
+      ts = group_sum(ts, G);
+      const S c0 = A_AT(k, k);
+      S beta, tk, den;
+      const bool degenerate = ts <= ST<S>::tiny();
+      if (degenerate) { tk = 0; beta = c0; den = S(1); }
+      else {
+        beta = sqrt(c0 * c0 + ts);
+        if (c0 >= S(0)) beta = -beta;
+        den = c0 - beta;
+        tk = (beta - c0) / beta;
+      }
+      tau[k] = tk;
+      // tmp_c = essential^T bottom + row k   for the remaining columns
+      S tmp[3] = {0, 0, 0};
+      for (int rho = j; rho < nrows; rho += G) {
+        if (rho > k) {
+          const S v = degenerate ? S(0) : A_AT(rho, k) / den;
+#pragma unroll
+          for (int c = 1; c <= 3; ++c) if (k + c <= 3) tmp[c - 1] += v * A_AT(rho, k + c);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmp[c] = group_sum(tmp[c], G);
+#pragma unroll
+      for (int c = 1; c <= 3; ++c) if (k + c <= 3) tmp[c - 1] += A_AT(k, k + c);
+      __syncwarp();
+      for (int rho = j; rho < nrows; rho += G) {
+        S v;
+        if (rho < k) v = 0;
+        else if (rho == k) {
+          v = 1;
+          A_AT(k, k) = beta;
+          if (tk != S(0))
+#pragma unroll
+            for (int c = 1; c <= 3; ++c) if (k + c <= 3) A_AT(k, k + c) -= tk * tmp[c - 1];
+        } else {
+          v = degenerate ? S(0) : A_AT(rho, k) / den;
+          if (tk != S(0)) {
+            const S te = tk * v;
+#pragma unroll
+            for (int c = 1; c <= 3; ++c) if (k + c <= 3) A_AT(rho, k + c) -= te * tmp[c - 1];
+          }
+        }
+        sV[3 * rho + k] = v;
+      }
+      __syncwarp();
+    }
+    S g10 = 0, g20 = 0, g21 = 0;
+    for (int rho = j; rho < nrows; rho += G) {
+      const S v0 = sV[3 * rho], v1 = sV[3 * rho + 1], v2 = sV[3 * rho + 2];
+      g10 += v1 * v0; g20 += v2 * v0; g21 += v2 * v1;
+    }
+    g10 = group_sum(g10, G); g20 = group_sum(g20, G); g21 = group_sum(g21, G);
+    if (active && j == 0) {
+      S* lk = D.lmk + 24 * (size_t)sidx;
+      lk[0] = A_AT(0, 0); lk[1] = A_AT(0, 1); lk[2] = A_AT(0, 2);
+      lk[3] = A_AT(1, 1); lk[4] = A_AT(1, 2); lk[5] = A_AT(2, 2);
+      lk[6] = A_AT(0, 3); lk[7] = A_AT(1, 3); lk[8] = A_AT(2, 3);
+      lk[18] = jls[0]; lk[19] = jls[1]; lk[20] = jls[2];
+    }
+#undef A_AT
+    // ---- d. apply Q^T = H2 H1 H0 to the block-diagonal Jp (compact WY) and write q1u + panel ----
+    V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off);
+    const int ncols = 9 * n;
+#pragma unroll 1
+    for (int k = 0; k < KP; ++k) {
+      const int c0 = 2 * j + 2 * G * k;
+      S a0[2], a1[2], w0[2], w1[2], w2[2];
+      int r2i[2], oi[2], op[2];
+      bool vc[2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int c = c0 + v;
+        vc[v] = c < ncols;
+        const int i = vc[v] ? c / 9 : 0;
+        const int p = vc[v] ? c - 9 * i : 0;
+        oi[v] = i; op[v] = p; r2i[v] = 2 * i;
+        a0[v] = vc[v] ? sJ[26 * i + p] : S(0);
+        a1[v] = vc[v] ? sJ[26 * i + 9 + p] : S(0);
+        const S* va = sV + 3 * (2 * i);
+        const S z0 = va[0] * a0[v] + va[3] * a1[v];
+        const S z1 = va[1] * a0[v] + va[4] * a1[v];
+        const S z2 = va[2] * a0[v] + va[5] * a1[v];
+        w0[v] = tau[0] * z0;
+        w1[v] = tau[1] * (z1 - g10 * w0[v]);
+        w2[v] = tau[2] * (z2 - g20 * w0[v] - g21 * w1[v]);
+      }
+      for (int r = 0; r < nrows; ++r) {
+        const S v0 = sV[3 * r], v1 = sV[3 * r + 1], v2 = sV[3 * r + 2];
+        S out[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const S sel = (r == r2i[v]) ? a0[v] : ((r == r2i[v] + 1) ? a1[v] : S(0));
+          out[v] = sel - (w0[v] * v0 + w1[v] * v1 + w2[v] * v2);
+        }
+        if (r < 3) {
+          if (active) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v)
+              if (vc[v]) D.q1u[27 * (size_t)(slot0 + oi[v]) + 9 * r + op[v]] = out[v];
+          }
+        } else if (active) {
+          ptile[((size_t)(r - 3) * KP + k) * 32 + lane] = mk2(vc[0] ? out[0] : S(0), vc[1] ? out[1] : S(0));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  stage 2: Givens landmark damping, RCS gradient (ref: ipp:638-658 = :165-210, :443-466)
+//   The 6 rotations only mix the 3 Q1 rows with the 3 damping rows, so each panel column is an
+//   independent 6-vector: q1d and the 3 damping rows are recomputed from the undamped q1u (instead of
+//   un-doing the previous rotations, ipp:175-186).  The gradient uses orthogonality of [Q1d; P]:
+//   P^T (Q2^T r) = Jp^T r - Q1d^T (Q1^T r)_d.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+struct Rot { S c, s; };
+
+template <class S>
+__device__ __forceinline__ Rot<S> make_givens(S p, S q) {  // Eigen JacobiRotation::makeGivens
+  Rot<S> g;
+  if (q == S(0)) { g.c = p < S(0) ? S(-1) : S(1); g.s = 0; }
+  else if (p == S(0)) { g.c = 0; g.s = q < S(0) ? S(1) : S(-1); }
+  else if (fabs(p) > fabs(q)) {
+    const S t = q / p; S u = sqrt(S(1) + t * t); if (p < S(0)) u = -u;
+    g.c = S(1) / u; g.s = -t * g.c;
+  } else {
+    const S t = p / q; S u = sqrt(S(1) + t * t); if (q < S(0)) u = -u;
+    g.s = -S(1) / u; g.c = -t * g.s;
+  }
+  return g;
+}
+// applyOnTheLeft(p=damping row, q=row n): x' = c x + s y ; y' = -s x + c y
+template <class S>
+__device__ __forceinline__ void rot_apply(const Rot<S>& g, S& x, S& y) {
+  const S xi = x, yi = y;
+  x = g.c * xi + g.s * yi;
+  y = -g.s * xi + g.c * yi;
+}
+
+template <class S>
+__global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda) {
+  using V2 = typename ST<S>::V2;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+    const TileInfo T = D.tiles[t];
+    const int n = T.n, G = T.G, KP = T.KP;
+    const int g = lane / G, j = lane - g * G;
+    const bool active = g < T.nvalid;
+    const int slot0 = T.slot_base + g * n;
+    const int sidx = T.lm_base + g;
+    // rotations from R (3x3 upper) and sqrt(lambda) (ref: ipp:188-209)
+    Rot<S> rot[6];
+    S Rw[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Dw[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    S rr[3] = {0, 0, 0}, dr[3] = {0, 0, 0};
+    if (active) {
+      const S* lk = D.lmk + 24 * (size_t)sidx;
+      Rw[0][0] = lk[0]; Rw[0][1] = lk[1]; Rw[0][2] = lk[2]; Rw[1][1] = lk[3]; Rw[1][2] = lk[4]; Rw[2][2] = lk[5];
+      rr[0] = lk[6]; rr[1] = lk[7]; rr[2] = lk[8];
+    }
+    if (lambda == S(0)) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) { rot[q].c = 1; rot[q].s = 0; }
+    } else {
+      const S sl = sqrt(lambda);
+      Dw[0][0] = sl; Dw[1][1] = sl; Dw[2][2] = sl;
+      int q = 0;
+#pragma unroll
+      for (int nn = 0; nn < 3; ++nn)
+#pragma unroll
+        for (int m = 0; m <= nn; ++m) {
+          const int d = nn - m;
+          const Rot<S> gq = make_givens(Rw[nn][nn], Dw[d][nn]);
+          rot[q++] = gq;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rot_apply(gq, Dw[d][c], Rw[nn][c]);
+          rot_apply(gq, dr[d], rr[nn]);
+        }
+    }
+    if (active && j == 0) {
+      S* lk = D.lmk + 24 * (size_t)sidx;
+      lk[9] = Rw[0][0]; lk[10] = Rw[0][1]; lk[11] = Rw[0][2]; lk[12] = Rw[1][1]; lk[13] = Rw[1][2]; lk[14] = Rw[2][2];
+      lk[15] = rr[0]; lk[16] = rr[1]; lk[17] = rr[2];
+    }
+    V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off);
+    const int ncols = 9 * n;
+    for (int k = 0; k < KP; ++k) {
+      const int c0 = 2 * j + 2 * G * k;
+      S drow[3][2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int c = c0 + v;
+        const bool vc = active && c < ncols;
+        S qv[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
+        if (vc) {
+          const int i = c / 9, p = c - 9 * i;
+          const size_t s = (size_t)(slot0 + i);
+          const S* qu = D.q1u + 27 * s + p;
+          qv[0] = qu[0]; qv[1] = qu[9]; qv[2] = qu[18];
+          int q = 0;
+#pragma unroll
+          for (int nn = 0; nn < 3; ++nn)
+#pragma unroll
+            for (int m = 0; m <= nn; ++m) rot_apply(rot[q++], dv[nn - m], qv[nn]);
+          S* rc = D.rec + 48 * s;
+          rc[18 + p] = qv[0]; rc[27 + p] = qv[1]; rc[36 + p] = qv[2];
+          // gradient of the reduced system: b_c = jp_c^T r_i - q1d_c^T (Q1^T r)_d
+          const S gc = rc[p] * D.res[2 * s] + rc[9 + p] * D.res[2 * s + 1] - (qv[0] * rr[0] + qv[1] * rr[1] + qv[2] * rr[2]);
+          D.yobs[9 * s + p] = gc;
+        }
+        drow[0][v] = dv[0]; drow[1][v] = dv[1]; drow[2][v] = dv[2];
+      }
+      if (active) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          ptile[((size_t)(2 * n - 3 + d) * KP + k) * 32 + lane] = mk2(drow[d][0], drow[d][1]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3a  block-Jacobi preconditioner blocks, camera-major (ref: ipp:520-552 SCHUR_JACOBI, :554-569 JACOBI)
+//   (Q2^T Jp)_i^T (Q2^T Jp)_i = Jp_i^T Jp_i - (Q1d^T Jp)_i^T (Q1d^T Jp)_i  (Q orthogonal, Givens on 6 rows)
+//   thread per ReduceItem chunk of <= 32 observations ... here: one thread per (item, 8-slot subchunk) would
+//   be finer; we use thread per item-of-32 built on the host (pb_items).
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(128) k_precond_partial(const S* __restrict__ rec, const int* __restrict__ slots,
+                                                          const ReduceItem* __restrict__ items, int nitems,
+                                                          int schur, S* __restrict__ pblk) {
+  using V4 = typename ST<S>::V4;
+  const int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= nitems) return;
+  const ReduceItem I = items[it];
+  S acc[45];
+#pragma unroll
+  for (int k = 0; k < 45; ++k) acc[k] = 0;
+  for (int e = I.begin; e < I.end; ++e) {
+    const V4* rp = reinterpret_cast<const V4*>(rec + 48 * (size_t)slots[e]);
+    S v[48];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+      const V4 t = rp[q];
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+      for (int b = a; b < 9; ++b) {
+        S s = v[a] * v[b] + v[9 + a] * v[9 + b];
+        if (schur) s -= v[18 + a] * v[18 + b] + v[27 + a] * v[27 + b] + v[36 + a] * v[36 + b];
+        acc[k++] += s;
+      }
+  }
+  S* o = pblk + 48 * (size_t)it;
+#pragma unroll
+  for (int k = 0; k < 45; ++k) o[k] = acc[k];
+}
+
+// blocks[cam][81] = sum of partial upper triangles (symmetrised)
+template <class S>
+__global__ void k_precond_final(const S* __restrict__ pblk, const int* __restrict__ cam_item_ptr, int nc,
+                                S* __restrict__ blocks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 45 * nc) return;
+  const int cam = i / 45, k = i - 45 * cam;
+  S s = 0;
+  for (int it = cam_item_ptr[cam]; it < cam_item_ptr[cam + 1]; ++it) s += pblk[48 * (size_t)it + k];
+  int a = 0, rem = k;
+  while (rem >= 9 - a) { rem -= 9 - a; ++a; }
+  const int b = a + rem;
+  blocks[81 * (size_t)cam + 9 * a + b] = s;
+  blocks[81 * (size_t)cam + 9 * b + a] = s;
+}
+
+// K3b  (blocks + lambda I) -> explicit inverse via Cholesky (ref: cg/preconditioner.hpp:79-120; pose damping
+//      linearization_qr.hpp:796-802 / linearizor_qr.cpp:228-232).  thread per camera.
+template <class S>
+__global__ void __launch_bounds__(64) k_precond_invert(const S* __restrict__ src, S lambda, int nc,
+                                                        S* __restrict__ blocks_out, S* __restrict__ inv) {
+  const int cam = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cam >= nc) return;
+  S A[81], L[81];
+#pragma unroll 1
+  for (int k = 0; k < 81; ++k) { A[k] = src[81 * (size_t)cam + k]; L[k] = 0; }
+#pragma unroll 1
+  for (int d = 0; d < 9; ++d) A[10 * d] += lambda;
+  if (blocks_out)
+#pragma unroll 1
+    for (int k = 0; k < 81; ++k) blocks_out[81 * (size_t)cam + k] = A[k];
+#pragma unroll 1
+  for (int jj = 0; jj < 9; ++jj) {
+    S s = A[10 * jj];
+    for (int k = 0; k < jj; ++k) s -= L[9 * jj + k] * L[9 * jj + k];
+    const S d = sqrt(s);
+    L[10 * jj] = d;
+    for (int i = jj + 1; i < 9; ++i) {
+      S t = A[9 * jj + i];
+      for (int k = 0; k < jj; ++k) t -= L[9 * i + k] * L[9 * jj + k];
+      L[9 * i + jj] = t / d;
+    }
+  }
+  S* out = inv + 81 * (size_t)cam;
+#pragma unroll 1
+  for (int col = 0; col < 9; ++col) {
+    S yv[9];
+    for (int i = 0; i < 9; ++i) {
+      S t = (i == col) ? S(1) : S(0);
+      for (int k = 0; k < i; ++k) t -= L[9 * i + k] * yv[k];
+      yv[i] = t / L[10 * i];
+    }
+    for (int i = 8; i >= 0; --i) {
+      S t = yv[i];
+      for (int k = i + 1; k < 9; ++k) t -= L[9 * k + i] * out[9 * k + col];
+      out[9 * i + col] = t / L[10 * i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  rcs_matvec: y_obs = P^T (P x_red) per landmark, P = dense Q2^T Jp panel (2n x 9n)
+//   ref: qr/impl/landmark_block_base.ipp:400-441 under qr/linearization_qr.hpp:406-429
+//   Warp per MatvecItem; lanes own panel columns; the panel is streamed exactly once with coalesced
+//   2-scalar vector loads; row dot products are reduced with log2(G) shuffles; x is gathered and y is
+//   written through a per-warp shared-memory transpose so that both are coalesced.
+// ------------------------------------------------------------------------------------------------
+template <class S, int KP>
+__device__ __forceinline__ void matvec_item(const DevPtrs<S>& D, const MatvecItem& it, const TileInfo& T, int lane,
+                                            S* xs, const S* __restrict__ xvec) {
+  using V2 = typename ST<S>::V2;
+  const int n = T.n, G = T.G;
+  const int g = lane / G, j = lane - g * G, W = 32 / G;
+  const int ncols = 9 * n;
+  const int CS = (2 * G * KP) | 1;
+  // zero padding columns, gather x_red of the W landmarks (coalesced runs of 9)
+  for (int e = lane; e < W * CS; e += 32) xs[e] = 0;
+  __syncwarp();
+  {
+    int g2 = 0, c = lane;
+    while (c >= ncols) { c -= ncols; ++g2; }
+    while (g2 < T.nvalid) {
+      const int i = c / 9, p = c - 9 * i;
+      const int cam = D.slot_cam[T.slot_base + g2 * n + i];
+      xs[g2 * CS + c] = xvec[9 * (size_t)cam + p];
+      c += 32;
+      while (c >= ncols) { c -= ncols; ++g2; }
+    }
+  }
+  __syncwarp();
+  V2 xv[KP], yv[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const int c = 2 * j + 2 * G * k;
+    xv[k] = mk2(xs[g * CS + c], xs[g * CS + c + 1]);
+    yv[k] = mk2(S(0), S(0));
+  }
+  __syncwarp();
+  const V2* __restrict__ prow = reinterpret_cast<const V2*>(D.panel + T.panel_off) + (size_t)it.row0 * KP * 32 + lane;
+  const int nrows = it.nrows;
+#pragma unroll 2
+  for (int r = 0; r < nrows; ++r) {
+    V2 v[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) v[k] = __ldg(prow + (size_t)(r * KP + k) * 32);
+    S d = 0;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) d += v[k].x * xv[k].x + v[k].y * xv[k].y;
+    d = group_sum(d, G);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { yv[k].x += d * v[k].x; yv[k].y += d * v[k].y; }
+  }
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const int c = 2 * j + 2 * G * k;
+    xs[g * CS + c] = yv[k].x;
+    xs[g * CS + c + 1] = yv[k].y;
+  }
+  __syncwarp();
+  {
+    int g2 = 0, c = lane;
+    while (c >= ncols) { c -= ncols; ++g2; }
+    while (g2 < T.nvalid) {
+      D.yobs[9 * (size_t)(it.yslot_base + g2 * n) + c] = xs[g2 * CS + c];
+      c += 32;
+      while (c >= ncols) { c -= ncols; ++g2; }
+    }
+  }
+  __syncwarp();
+}
+
+// generic variant for very long tracks (KP beyond the register-resident classes): x and y live in shared memory
+template <class S>
+__device__ __forceinline__ void matvec_item_generic(const DevPtrs<S>& D, const MatvecItem& it, const TileInfo& T,
+                                                    int lane, S* xs, const S* __restrict__ xvec) {
+  using V2 = typename ST<S>::V2;
+  const int n = T.n, KP = T.KP;  // G == 32, W == 1
+  const int ncols = 9 * n, CP = 64 * KP;
+  S* ys = xs + CP;
+  for (int c = lane; c < CP; c += 32) {
+    S v = 0;
+    if (c < ncols) {
+      const int i = c / 9, p = c - 9 * i;
+      v = xvec[9 * (size_t)D.slot_cam[T.slot_base + i] + p];
+    }
+    xs[c] = v;
+    ys[c] = 0;
+  }
+  __syncwarp();
+  const V2* __restrict__ prow = reinterpret_cast<const V2*>(D.panel + T.panel_off) + (size_t)it.row0 * KP * 32 + lane;
+  for (int r = 0; r < it.nrows; ++r) {
+    S d = 0;
+    for (int k = 0; k < KP; ++k) {
+      const V2 v = __ldg(prow + (size_t)(r * KP + k) * 32);
+      const int c = 2 * lane + 64 * k;
+      d += v.x * xs[c] + v.y * xs[c + 1];
+    }
+    d = warp_sum(d);
+    for (int k = 0; k < KP; ++k) {
+      const V2 v = __ldg(prow + (size_t)(r * KP + k) * 32);  // second touch hits L1/L2
+      const int c = 2 * lane + 64 * k;
+      ys[c] += d * v.x;
+      ys[c + 1] += d * v.y;
+    }
+  }
+  __syncwarp();
+  for (int c = lane; c < ncols; c += 32) D.yobs[9 * (size_t)it.yslot_base + c] = ys[c];
+  __syncwarp();
+}
+
+template <class S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_matvec_small(DevPtrs<S> D, const MatvecItem* __restrict__ items,
+                                                              int item_begin, int item_end, int scratch_per_warp,
+                                                              const S* __restrict__ xvec, const int* done) {
+  if (done && *done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  S* xs = reinterpret_cast<S*>(smem_raw) + (size_t)wib * scratch_per_warp;
+  for (int q = item_begin + blockIdx.x * WARPS + wib; q < item_end; q += gridDim.x * WARPS) {
+    const MatvecItem it = items[q];
+    const TileInfo T = D.tiles[it.tile];
+    switch (T.KP) {
+      case 5: matvec_item<S, 5>(D, it, T, lane, xs, xvec); break;
+      case 6: matvec_item<S, 6>(D, it, T, lane, xs, xvec); break;
+      case 7: matvec_item<S, 7>(D, it, T, lane, xs, xvec); break;
+      case 8: matvec_item<S, 8>(D, it, T, lane, xs, xvec); break;
+      case 9: matvec_item<S, 9>(D, it, T, lane, xs, xvec); break;
+      default: break;
+    }
+  }
+}
+
+template <class S, int WARPS, int KPMAX>
+__global__ void __launch_bounds__(WARPS * 32) k_matvec_large(DevPtrs<S> D, const MatvecItem* __restrict__ items,
+                                                              int item_begin, int item_end, int scratch_per_warp,
+                                                              const S* __restrict__ xvec, const int* done) {
+  if (done && *done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  S* xs = reinterpret_cast<S*>(smem_raw) + (size_t)wib * scratch_per_warp;
+  for (int q = item_begin + blockIdx.x * WARPS + wib; q < item_end; q += gridDim.x * WARPS) {
+    const MatvecItem it = items[q];
+    const TileInfo T = D.tiles[it.tile];
+    if (T.KP == 10) matvec_item<S, 10>(D, it, T, lane, xs, xvec);
+    else if (KPMAX >= 12 && T.KP == 12) matvec_item<S, (KPMAX >= 12 ? 12 : 10)>(D, it, T, lane, xs, xvec);
+    else if (KPMAX >= 14 && T.KP == 14) matvec_item<S, (KPMAX >= 14 ? 14 : 10)>(D, it, T, lane, xs, xvec);
+    else if (KPMAX >= 16 && T.KP == 16) matvec_item<S, (KPMAX >= 16 ? 16 : 10)>(D, it, T, lane, xs, xvec);
+    else matvec_item_generic<S>(D, it, T, lane, xs, xvec);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PCG vector kernels (ref: cg/conjugate_gradient.hpp:113-298, cg/preconditioner.hpp:122-136)
+//   all launched with exactly NPART blocks of 128 threads; thread per camera (9-vectors);
+//   partial sums per block in double, combined in a fixed order by the consumer kernel.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__device__ __forceinline__ void precond_apply(const S* __restrict__ inv_cam, const S* rv, S* zv) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    S a = 0;
+#pragma unroll
+    for (int jj = 0; jj < 9; ++jj) a += inv_cam[9 * i + jj] * rv[jj];
+    zv[i] = a;
+  }
+}
+
+// init: x = 0, r = b, z = M^-1 r ; partials [rz, bb, xbr=0]
+template <class S>
+__global__ void __launch_bounds__(128) k_pcg_init(DevPtrs<S> D, PcgState* st, double* part) {
+  double acc[3] = {0, 0, 0};
+  for (int cam = blockIdx.x * blockDim.x + threadIdx.x; cam < D.nc; cam += gridDim.x * blockDim.x) {
+    S rv[9], zv[9];
+#pragma unroll
+    for (int c = 0; c < 9; ++c) rv[c] = D.b[9 * (size_t)cam + c];
+    precond_apply(D.inv + 81 * (size_t)cam, rv, zv);
+    S rz = 0, bb = 0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      D.x[9 * (size_t)cam + c] = 0;
+      D.r[9 * (size_t)cam + c] = rv[c];
+      D.z[9 * (size_t)cam + c] = zv[c];
+      rz += rv[c] * zv[c];
+      bb += rv[c] * rv[c];
+    }
+    acc[0] += (double)rz; acc[1] += (double)bb;
+  }
+  block_sum_store<3>(acc, part);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    st->rho[0] = 1.0; st->rho[1] = 1.0; st->q0[0] = 0.0; st->q0[1] = 0.0;
+    st->iter = 0; st->done = 0; st->term = 0; st->reason = 0; st->norm_b = 0;
+  }
+}
+
+// begin iteration i: convergence test of iteration i-1, rho, beta, p update.
+// finish = 1: only evaluate the pending test (after the last iteration) and write inc = -x.
+template <class S>
+__global__ void __launch_bounds__(128) k_pcg_begin(DevPtrs<S> D, PcgState* st, const double* part, int i, double eta,
+                                                   int min_it, int finish) {
+  int done = st->done;
+  const int cur = i & 1, prev = cur ^ 1;
+  double rho = 0, beta = 0;
+  int term = 0, reason = 0;
+  double q1 = 0, zeta = 0, norm_b = 0;
+  if (!done) {
+    rho = block_sum_partials(part, NPART, 3, 0);
+    const double xbr = block_sum_partials(part, NPART, 3, 2);
+    if (i == 1) {
+      norm_b = sqrt(block_sum_partials(part, NPART, 3, 1));
+      if (norm_b == 0.0) { done = 1; term = 1; reason = 2; }
+    } else {
+      q1 = -xbr;
+      zeta = (double)(i - 1) * (q1 - st->q0[prev]) / q1;
+      if (zeta < eta && (i - 1) >= min_it) { done = 1; term = 1; reason = 1; }
+    }
+    if (!done && !finish) {
+      if (rho == 0.0 || isinf(rho)) { done = 1; term = 2; reason = 3; }
+      else if (i > 1) {
+        beta = rho / st->rho[prev];
+        if (beta == 0.0 || isinf(beta)) { done = 1; term = 2; reason = 4; }
+      }
+    }
+    if (!done && !finish) {
+      const S bs = (S)beta;
+      for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 9 * D.nc; k += gridDim.x * blockDim.x)
+        D.p[k] = (i == 1) ? D.z[k] : D.z[k] + bs * D.p[k];
+    }
+  }
+  if (finish) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 9 * D.nc; k += gridDim.x * blockDim.x) D.inc[k] = -D.x[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !st->done) {
+    if (i == 1) st->norm_b = norm_b;
+    st->rho[cur] = rho;
+    st->q0[cur] = (i == 1) ? 0.0 : q1;
+    st->last_zeta = zeta;
+    if (done) { st->done = 1; st->term = term; st->reason = reason; }
+    else if (!finish) st->iter = i;
+  }
+}
+
+// q = (sum of camera partials | y) + lambda p ; partial pq.   src9 = y vector [9nc] (already reduced)
+template <class S>
+__global__ void __launch_bounds__(128) k_pcg_q(DevPtrs<S> D, const PcgState* st, const S* __restrict__ partial,
+                                               const int* __restrict__ cam_item_ptr, const S* __restrict__ yfull,
+                                               const S* __restrict__ vec, S* __restrict__ out, S lambda, double* part) {
+  if (st && st->done) return;
+  double acc[1] = {0};
+  for (int cam = blockIdx.x * blockDim.x + threadIdx.x; cam < D.nc; cam += gridDim.x * blockDim.x) {
+    S yv[9];
+    if (yfull) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) yv[c] = yfull[9 * (size_t)cam + c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) yv[c] = 0;
+      for (int it = cam_item_ptr[cam]; it < cam_item_ptr[cam + 1]; ++it)
+#pragma unroll
+        for (int c = 0; c < 9; ++c) yv[c] += partial[9 * (size_t)it + c];
+    }
+    S pq = 0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      const S pv = vec[9 * (size_t)cam + c];
+      const S qv = yv[c] + lambda * pv;
+      out[9 * (size_t)cam + c] = qv;
+      pq += pv * qv;
+    }
+    acc[0] += (double)pq;
+  }
+  if (part) block_sum_store<1>(acc, part);
+}
+
+// y_local = sum of camera partials (multi-GPU: feeds the all-reduce)
+template <class S>
+__global__ void k_cam_final9(const S* __restrict__ partial, const int* __restrict__ cam_item_ptr, int nc,
+                             S* __restrict__ out, const int* done) {
+  if (done && *done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * nc) return;
+  const int cam = i / 9, c = i - 9 * cam;
+  S s = 0;
+  for (int it = cam_item_ptr[cam]; it < cam_item_ptr[cam + 1]; ++it) s += partial[9 * (size_t)it + c];
+  out[i] = s;
+}
+
+// mode 0: alpha = rho/pq ; x += alpha p ; r -= alpha q ; z = M^-1 r ; partials [rz, -, x.(b+r)]
+// mode 1: (refresh iteration, first half) alpha ; x += alpha p only
+// mode 2: (refresh iteration, second half) r = b - q (q = H x) ; z ; partials
+template <class S>
+__global__ void __launch_bounds__(128) k_pcg_update(DevPtrs<S> D, PcgState* st, const double* part_pq, double* part,
+                                                    int i, int mode) {
+  if (st->done) return;
+  double alpha = 0;
+  bool fail = false;
+  int term = 0, reason = 0;
+  double pq = 0;
+  if (mode != 2) {
+    pq = block_sum_partials(part_pq, NPART, 1, 0);
+    if (pq <= 0 || isinf(pq)) { fail = true; term = 0; reason = 5; }
+    else {
+      alpha = st->rho[i & 1] / pq;
+      if (isinf(alpha)) { fail = true; term = 2; reason = 6; }
+    }
+  }
+  if (fail) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->done = 1; st->term = term; st->reason = reason; st->last_pq = pq; }
+    return;
+  }
+  const S as = (S)alpha;
+  double acc[3] = {0, 0, 0};
+  for (int cam = blockIdx.x * blockDim.x + threadIdx.x; cam < D.nc; cam += gridDim.x * blockDim.x) {
+    const size_t o = 9 * (size_t)cam;
+    S xv[9], rv[9], zv[9];
+    if (mode == 1) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) D.x[o + c] = D.x[o + c] + as * D.p[o + c];
+      continue;
+    }
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      if (mode == 0) {
+        xv[c] = D.x[o + c] + as * D.p[o + c];
+        rv[c] = D.r[o + c] - as * D.q[o + c];
+        D.x[o + c] = xv[c];
+      } else {
+        xv[c] = D.x[o + c];
+        rv[c] = D.b[o + c] - D.q[o + c];
+      }
+      D.r[o + c] = rv[c];
+    }
+    precond_apply(D.inv + 81 * (size_t)cam, rv, zv);
+    S rz = 0, xbr = 0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      D.z[o + c] = zv[c];
+      rz += rv[c] * zv[c];
+      xbr += xv[c] * (D.b[o + c] + rv[c]);
+    }
+    acc[0] += (double)rz; acc[2] += (double)xbr;
+  }
+  if (mode != 1) block_sum_store<3>(acc, part);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && mode != 2) { st->last_pq = pq; st->last_alpha = alpha; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  back-substitution (ref: ipp:212-284).  Model-cost change evaluated in the un-rotated basis:
+//     Q^T (Jp dp + Jl inc) has the same norm / inner product with Q^T r as (Jp dp + Jl inc) with r.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* __restrict__ pose_inc,
+                                                          double* partials, int* bad_flag) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double ld[1] = {0};
+  for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+    const TileInfo T = D.tiles[t];
+    const int n = T.n, G = T.G;
+    const int g = lane / G, j = lane - g * G;
+    const bool active = g < T.nvalid;
+    const int slot0 = T.slot_base + g * n;
+    const int sidx = T.lm_base + g;
+    // s_m = sum_c q1d[m][c] dp[c]
+    S sm[3] = {0, 0, 0};
+    if (active) {
+      for (int i = j; i < n; i += G) {
+        const size_t s = (size_t)(slot0 + i);
+        const S* dp = pose_inc + 9 * (size_t)D.slot_cam[s];
+        const S* rc = D.rec + 48 * s;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+          const S d = dp[c];
+          sm[0] += rc[18 + c] * d; sm[1] += rc[27 + c] * d; sm[2] += rc[36 + c] * d;
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) sm[m] = group_sum(sm[m], G);
+    S inc[3] = {0, 0, 0}, jls[3] = {0, 0, 0};
+    if (active) {
+      const S* lk = D.lmk + 24 * (size_t)sidx;
+      const S rhs0 = lk[15] + sm[0], rhs1 = lk[16] + sm[1], rhs2 = lk[17] + sm[2];
+      // upper-triangular solve with the damped R (Eigen triangularView<Upper>().solve)
+      const S s2 = rhs2 / lk[14];
+      const S s1 = (rhs1 - lk[13] * s2) / lk[12];
+      const S s0 = (rhs0 - lk[10] * s1 - lk[11] * s2) / lk[9];
+      inc[0] = -s0; inc[1] = -s1; inc[2] = -s2;
+      jls[0] = lk[18]; jls[1] = lk[19]; jls[2] = lk[20];
+    }
+    S lpart = 0;
+    if (active) {
+      for (int i = j; i < n; i += G) {
+        const size_t s = (size_t)(slot0 + i);
+        const S* dp = pose_inc + 9 * (size_t)D.slot_cam[s];
+        const S* rc = D.rec + 48 * s;
+        const S* jl = D.jl + 6 * s;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          S ji = 0;
+#pragma unroll
+          for (int c = 0; c < 9; ++c) ji += rc[9 * rr + c] * dp[c];
+          ji += jl[3 * rr] * inc[0] + jl[3 * rr + 1] * inc[1] + jl[3 * rr + 2] * inc[2];
+          lpart += ji * (S(0.5) * ji + D.res[2 * s + rr]);
+        }
+      }
+    }
+    lpart = group_sum(lpart, G);
+    if (active && j == 0) {
+      ld[0] -= (double)lpart;
+      const int lm = D.sorted_lm[sidx];
+      S* pw = D.lms + 3 * (size_t)lm;
+      const bool ok = finite_s(inc[0]) && finite_s(inc[1]) && finite_s(inc[2]) && finite_s(pw[0]) && finite_s(pw[1]) && finite_s(pw[2]);
+      if (!ok) atomicOr(bad_flag, 1);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) pw[d] += inc[d] * jls[d];
+    }
+  }
+  block_sum_store<1>(ld, partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  camera update (ref: solver/linearizor_qr.cpp:279-287, bal/bal_problem.hpp:97-109, Sophus se3_expd / SO3::exp)
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void k_camera_update(DevPtrs<S> D, const S* __restrict__ inc) {
+  const int cam = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cam >= D.nc) return;
+  S v[9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) v[c] = inc[9 * (size_t)cam + c] * D.scaling[9 * (size_t)cam + c];
+  S* cm = D.cams + 10 * (size_t)cam;
+  // SO3::exp
+  const S th2 = v[3] * v[3] + v[4] * v[4] + v[5] * v[5];
+  S imag, real;
+  if (th2 < ST<S>::eps() * ST<S>::eps()) {
+    const S th4 = th2 * th2;
+    imag = S(0.5) - S(1.0 / 48.0) * th2 + S(1.0 / 3840.0) * th4;
+    real = S(1) - S(1.0 / 8.0) * th2 + S(1.0 / 384.0) * th4;
+  } else {
+    const S th = sqrt(th2);
+    const S half = S(0.5) * th;
+    imag = sin(half) / th;
+    real = cos(half);
+  }
+  const S qe[4] = {imag * v[3], imag * v[4], imag * v[5], real};
+  S Re[9];
+  quat_to_rot(qe, Re);
+  const S t0 = cm[4], t1 = cm[5], t2 = cm[6];
+  const S a0 = qe[0], a1 = qe[1], a2 = qe[2], a3 = qe[3];
+  const S b0 = cm[0], b1 = cm[1], b2 = cm[2], b3 = cm[3];
+  S rq[4];
+  rq[3] = a3 * b3 - a0 * b0 - a1 * b1 - a2 * b2;
+  rq[0] = a3 * b0 + a0 * b3 + a1 * b2 - a2 * b1;
+  rq[1] = a3 * b1 + a1 * b3 + a2 * b0 - a0 * b2;
+  rq[2] = a3 * b2 + a2 * b3 + a0 * b1 - a1 * b0;
+  const S sq = rq[0] * rq[0] + rq[1] * rq[1] + rq[2] * rq[2] + rq[3] * rq[3];
+  if (sq != S(1)) {
+    const S sc = S(2) / (S(1) + sq);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rq[k] *= sc;
+  }
+  cm[0] = rq[0]; cm[1] = rq[1]; cm[2] = rq[2]; cm[3] = rq[3];
+  cm[4] = Re[0] * t0 + Re[1] * t1 + Re[2] * t2 + v[0];
+  cm[5] = Re[3] * t0 + Re[4] * t1 + Re[5] * t2 + v[1];
+  cm[6] = Re[6] * t0 + Re[7] * t1 + Re[8] * t2 + v[2];
+  cm[7] += v[6]; cm[8] += v[7]; cm[9] += v[8];
+}
+
+}  // namespace rba

@@ -1,0 +1,729 @@
+// Host orchestration + C ABI (include/rootba_b200.h) of the B200-native square-root BA inner loop.
+// One rba_handle = one landmark shard on one GPU; everything is enqueued on one CUDA stream.
+// "ref:" citations are relative to /root/reference/src/rootba/.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/rootba_b200.h"
+#include "kernels.cuh"
+#include "nccl_dyn.hpp"
+
+namespace rba {
+
+thread_local std::string g_err;
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+      return RBA_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  bool used = false;
+};
+
+}  // namespace rba
+
+using namespace rba;
+
+// type-erased base so the C ABI can hold either scalar type
+struct rba_handle {
+  int scalar_size = 0;
+  virtual ~rba_handle() {}
+  virtual int set_state(const void* cams, const void* lms) = 0;
+  virtual int get_state(void* cams, void* lms) = 0;
+  virtual int backup() = 0;
+  virtual int restore() = 0;
+  virtual int compute_error(rba_residual_info* out) = 0;
+  virtual int linearize() = 0;
+  virtual int solve(double lambda, void* inc_out, rba_cg_summary* cg) = 0;
+  virtual int apply(const void* inc, void* l_diff_out, bool update_cameras) = 0;
+  virtual int get_timings(rba_stage_timings* out) const = 0;
+  virtual int get_stats(rba_workload_stats* out) const = 0;
+  virtual int get_scaling(void* scaling, void* diag2) = 0;
+  virtual int get_rhs(void* b) = 0;
+  virtual int get_precond(void* inv, void* blocks) = 0;
+  virtual int right_multiply(const void* x, void* y) = 0;
+  virtual int debug_get_block(int lm, void* out, int rows, int cols, void* jls) = 0;
+  virtual int time_matvec(int reps, double* sec) = 0;
+  virtual int timer_start() = 0;
+  virtual int timer_stop(double* sec) = 0;
+  virtual void* stream_ptr() = 0;
+  virtual int synchronize() = 0;
+  virtual int comm_init(const void* uid) = 0;
+};
+
+namespace rba {
+
+template <class S>
+struct Solver : rba_handle {
+  rba_solver_opts opt{};
+  KOpts ko{};
+  Layout L;
+  int nc = 0, nl_total = 0;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+  size_t device_bytes = 0;
+  DevPtrs<S> D{};
+  // device-only helpers
+  S* cams_bk = nullptr; S* lms_bk = nullptr;
+  MatvecItem* d_items = nullptr;
+  int* d_csr_obs_slots = nullptr; ReduceItem* d_csr_obs_items = nullptr; int* d_csr_obs_item_ptr = nullptr;
+  int* d_csr_y_slots = nullptr; ReduceItem* d_csr_y_items = nullptr; int* d_csr_y_item_ptr = nullptr;
+  int n_obs_items = 0, n_y_items = 0;
+  ReduceItem* d_pb_items = nullptr; int* d_pb_item_ptr = nullptr; int n_pb_items = 0;
+  double* d_part = nullptr;      // [NPART][3]
+  double* d_part_pq = nullptr;   // [NPART]
+  double* d_epart = nullptr;     // [EBLOCKS][6]
+  double* d_red = nullptr;       // [8] reduced doubles (error / l_diff)
+  int* d_flags = nullptr;        // [4] bad flags
+  PcgState* d_state = nullptr;
+  PcgState* h_state = nullptr;   // pinned [2]
+  double* h_red = nullptr;       // pinned [8]
+  int* h_flags = nullptr;        // pinned [4]
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+  // status
+  bool linearized = false;
+  bool new_linearization_point = false;
+  bool have_inc = false;
+  S last_lambda = 0;
+  bool damping_valid = false;
+  rba_stage_timings tm{};
+  EventPair ev_stage1, ev_stage2, ev_precond, ev_pcg, ev_backsub, ev_update, ev_error, ev_mv, ev_user;
+  long long launches = 0;
+  // NCCL
+  NcclApi* nccl = nullptr;
+  ncclComm_t comm = nullptr;
+  static constexpr int EBLOCKS = 592;
+  static constexpr int KPMAX = sizeof(S) == 4 ? 16 : 10;
+
+  ~Solver() override {
+    if (comm && nccl) nccl->CommDestroy(comm);
+    for (void* p : allocs) cudaFree(p);
+    if (h_state) cudaFreeHost(h_state);
+    if (h_red) cudaFreeHost(h_red);
+    if (h_flags) cudaFreeHost(h_flags);
+    for (EventPair* e : {&ev_stage1, &ev_stage2, &ev_precond, &ev_pcg, &ev_backsub, &ev_update, &ev_error, &ev_mv, &ev_user}) {
+      if (e->a) cudaEventDestroy(e->a);
+      if (e->b) cudaEventDestroy(e->b);
+    }
+    for (auto& e : poll_ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  template <class T>
+  int dalloc(T** p, size_t count, bool zero = true) {
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    void* q = nullptr;
+    CU(cudaMalloc(&q, bytes));
+    allocs.push_back(q);
+    device_bytes += bytes;
+    if (zero) CU(cudaMemsetAsync(q, 0, bytes, stream));
+    *p = (T*)q;
+    return RBA_OK;
+  }
+  template <class T>
+  int upload(T** p, const std::vector<T>& v) {
+    int rc = dalloc(p, v.size(), false);
+    if (rc) return rc;
+    if (!v.empty()) CU(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    return RBA_OK;
+  }
+
+  int start(EventPair& e) { e.used = true; CU(cudaEventRecord(e.a, stream)); return RBA_OK; }
+  int stop(EventPair& e) { CU(cudaEventRecord(e.b, stream)); return RBA_OK; }
+  static double elapsed(EventPair& e) {
+    if (!e.used) return 0.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) != cudaSuccess) return 0.0;
+    return 1e-3 * ms;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  int init(const rba_problem_view* pv, const rba_solver_opts* o) {
+    opt = *o;
+    if (opt.nranks < 1 || opt.rank < 0 || opt.rank >= opt.nranks) { g_err = "bad rank/nranks"; return RBA_ERR_INVALID_ARGUMENT; }
+    if (!opt.use_householder_marginalization) { g_err = "Givens marginalisation is not implemented on device"; return RBA_ERR_UNSUPPORTED; }
+    if (opt.pcg_check_period <= 0) opt.pcg_check_period = 4;
+    if (opt.residual_reset_period <= 0) opt.residual_reset_period = 10;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      g_err = "no CUDA device: rootba_b200 has no CPU fallback";
+      return RBA_ERR_NO_DEVICE;
+    }
+    if (opt.device >= 0) CU(cudaSetDevice(opt.device));
+    CU(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (EventPair* e : {&ev_stage1, &ev_stage2, &ev_precond, &ev_pcg, &ev_backsub, &ev_update, &ev_error, &ev_mv, &ev_user}) {
+      CU(cudaEventCreate(&e->a));
+      CU(cudaEventCreate(&e->b));
+    }
+    for (auto& e : poll_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    nc = pv->num_cameras;
+    nl_total = pv->num_landmarks;
+    ko.use_valid_projections_only = opt.use_valid_projections_only;
+    ko.robust_norm = opt.robust_norm;
+    ko.huber = opt.huber_parameter;
+    ko.jacobi_eps = opt.jacobi_scaling_epsilon > 0 ? opt.jacobi_scaling_epsilon : (double)ST<S>::eps_sqrt();  // ref: linearizor_base.cpp:72-79
+    std::string msg = build_layout(nc, nl_total, pv->lm_obs_offset, pv->obs_cam_idx, opt.rank, opt.nranks, KPMAX, L);
+    if (!msg.empty()) { g_err = msg; return RBA_ERR_INVALID_ARGUMENT; }
+    // observation coordinates in slot order
+    std::vector<S> xy((size_t)2 * L.nslots, S(0));
+    const S* src = (const S*)pv->obs_xy;
+    for (int s = 0; s < L.nslots; ++s)
+      if (L.slot_obs[s] >= 0) { xy[2 * (size_t)s] = src[2 * L.slot_obs[s]]; xy[2 * (size_t)s + 1] = src[2 * L.slot_obs[s] + 1]; }
+    int rc;
+    TileInfo* d_tiles; int* d_sorted; int* d_slot_cam; int* d_slot_lm; S* d_xy;
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    TRY(upload(&d_tiles, L.tiles));
+    TRY(upload(&d_sorted, L.sorted_lm));
+    TRY(upload(&d_slot_cam, L.slot_cam));
+    TRY(upload(&d_slot_lm, L.slot_lm));
+    TRY(upload(&d_xy, xy));
+    TRY(upload(&d_items, L.items));
+    TRY(upload(&d_csr_obs_slots, L.csr_obs.slots));
+    TRY(upload(&d_csr_obs_items, L.csr_obs.items));
+    TRY(upload(&d_csr_obs_item_ptr, L.csr_obs.cam_item_ptr));
+    n_obs_items = (int)L.csr_obs.items.size();
+    if (L.csr_y_is_obs) {
+      d_csr_y_slots = d_csr_obs_slots; d_csr_y_items = d_csr_obs_items; d_csr_y_item_ptr = d_csr_obs_item_ptr;
+      n_y_items = n_obs_items;
+    } else {
+      TRY(upload(&d_csr_y_slots, L.csr_y.slots));
+      TRY(upload(&d_csr_y_items, L.csr_y.items));
+      TRY(upload(&d_csr_y_item_ptr, L.csr_y.cam_item_ptr));
+      n_y_items = (int)L.csr_y.items.size();
+    }
+    TRY(upload(&d_pb_items, L.pb_items));
+    TRY(upload(&d_pb_item_ptr, L.pb_cam_item_ptr));
+    n_pb_items = (int)L.pb_items.size();
+    D.tiles = d_tiles; D.ntiles = (int)L.tiles.size(); D.sorted_lm = d_sorted;
+    D.slot_cam = d_slot_cam; D.slot_lm = d_slot_lm; D.slot_xy = d_xy; D.nslots = L.nslots; D.nc = nc;
+    TRY(dalloc(&D.cams, (size_t)10 * nc)); TRY(dalloc(&cams_bk, (size_t)10 * nc));
+    TRY(dalloc(&D.lms, (size_t)3 * L.nl_local)); TRY(dalloc(&lms_bk, (size_t)3 * L.nl_local));
+    TRY(dalloc(&D.panel, (size_t)L.panel_scalars));
+    TRY(dalloc(&D.rec, (size_t)48 * L.nslots));
+    TRY(dalloc(&D.q1u, (size_t)27 * L.nslots));
+    TRY(dalloc(&D.jl, (size_t)6 * L.nslots));
+    TRY(dalloc(&D.res, (size_t)2 * L.nslots));
+    TRY(dalloc(&D.lmk, (size_t)24 * L.sorted_lm.size()));
+    for (S** v : {&D.diag2, &D.scaling, &D.b, &D.x, &D.r, &D.z, &D.p, &D.q, &D.y, &D.inc}) TRY(dalloc(v, (size_t)9 * nc));
+    TRY(dalloc(&D.blocks, (size_t)81 * nc)); TRY(dalloc(&D.jblocks, (size_t)81 * nc)); TRY(dalloc(&D.inv, (size_t)81 * nc));
+    TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
+    TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
+    TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
+    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART));
+    TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
+    TRY(dalloc(&d_state, 1));
+#undef TRY
+    CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
+    CU(cudaMallocHost((void**)&h_red, 8 * sizeof(double)));
+    CU(cudaMallocHost((void**)&h_flags, 4 * sizeof(int)));
+    // shared-memory opt-in
+    k1_warps = 4;
+    while (k1_warps > 1 && (size_t)k1_warps * L.k1_scratch_per_warp * sizeof(S) > 200 * 1024) k1_warps >>= 1;
+    if ((size_t)k1_warps * L.k1_scratch_per_warp * sizeof(S) > 220 * 1024) {
+      g_err = "track length " + std::to_string(L.max_n) + " exceeds the shared-memory budget of the linearize+QR kernel";
+      return RBA_ERR_UNSUPPORTED;
+    }
+    k1_smem = (size_t)k1_warps * L.k1_scratch_per_warp * sizeof(S);
+    CU(cudaFuncSetAttribute(k_linearize_qr<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k1_smem, 1024)));
+    k4_smem_small = (size_t)K4_WARPS * L.k4_scratch_per_warp * sizeof(S);
+    if (k4_smem_small > 200 * 1024) { g_err = "matvec scratch exceeds shared memory"; return RBA_ERR_UNSUPPORTED; }
+    CU(cudaFuncSetAttribute(k_matvec_small<S, K4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k4_smem_small, 1024)));
+    CU(cudaFuncSetAttribute((k_matvec_large<S, K4_WARPS, KPMAX>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k4_smem_small, 1024)));
+    CU(cudaStreamSynchronize(stream));
+    return RBA_OK;
+  }
+  static constexpr int K4_WARPS = 4;
+  int k1_warps = 4;
+  size_t k1_smem = 0, k4_smem_small = 0;
+
+  // ------------------------------------------------------------------------------------------
+  int allreduce(void* buf, size_t count, bool is_double) {
+    if (opt.nranks == 1) return RBA_OK;
+    if (!comm) { g_err = "rba_comm_init has not been called on a sharded handle"; return RBA_ERR_STATE; }
+    ncclResult_t r = nccl->AllReduce(buf, buf, count, is_double ? ncclDouble : (sizeof(S) == 4 ? ncclFloat : ncclDouble), ncclSum, comm, stream);
+    if (r != ncclSuccess) { g_err = std::string("ncclAllReduce: ") + nccl->GetErrorString(r); return RBA_ERR_NCCL; }
+    return RBA_OK;
+  }
+  int allreduce_flags() {  // OR of the bad flags (sum of ints)
+    if (opt.nranks == 1) return RBA_OK;
+    ncclResult_t r = nccl->AllReduce(d_flags, d_flags, 4, ncclInt, ncclSum, comm, stream);
+    if (r != ncclSuccess) { g_err = std::string("ncclAllReduce: ") + nccl->GetErrorString(r); return RBA_ERR_NCCL; }
+    return RBA_OK;
+  }
+
+  int comm_init(const void* uid) override {
+    if (opt.nranks == 1) return RBA_OK;
+    nccl = nccl_api();
+    if (!nccl) { g_err = "libnccl.so.2 could not be loaded"; return RBA_ERR_NCCL; }
+    ncclUniqueId id;
+    std::memcpy(&id, uid, sizeof(id));
+    CU(cudaSetDevice(device));
+    ncclResult_t r = nccl->CommInitRank(&comm, opt.nranks, id, opt.rank);
+    if (r != ncclSuccess) { g_err = std::string("ncclCommInitRank: ") + nccl->GetErrorString(r); return RBA_ERR_NCCL; }
+    return RBA_OK;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  int set_state(const void* cams, const void* lms) override {
+    CU(cudaMemcpyAsync(D.cams, cams, (size_t)10 * nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(D.lms, (const S*)lms + (size_t)3 * L.lm_begin, (size_t)3 * L.nl_local * sizeof(S), cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));
+    return RBA_OK;
+  }
+  int get_state(void* cams, void* lms) override {
+    CU(cudaMemcpyAsync(cams, D.cams, (size_t)10 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync((S*)lms + (size_t)3 * L.lm_begin, D.lms, (size_t)3 * L.nl_local * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return RBA_OK;
+  }
+  int backup() override {  // ref: bal/bal_problem.cpp:590-598
+    CU(cudaMemcpyAsync(cams_bk, D.cams, (size_t)10 * nc * sizeof(S), cudaMemcpyDeviceToDevice, stream));
+    CU(cudaMemcpyAsync(lms_bk, D.lms, (size_t)3 * L.nl_local * sizeof(S), cudaMemcpyDeviceToDevice, stream));
+    return RBA_OK;
+  }
+  int restore() override {  // ref: bal/bal_problem.cpp:600-608
+    CU(cudaMemcpyAsync(D.cams, cams_bk, (size_t)10 * nc * sizeof(S), cudaMemcpyDeviceToDevice, stream));
+    CU(cudaMemcpyAsync(D.lms, lms_bk, (size_t)3 * L.nl_local * sizeof(S), cudaMemcpyDeviceToDevice, stream));
+    return RBA_OK;
+  }
+
+  int grid_for(long long work_items, int per_block, int blocks_per_sm) const {
+    long long g = (work_items + per_block - 1) / per_block;
+    g = std::min<long long>(g, (long long)sm_count * blocks_per_sm);
+    return (int)std::max<long long>(g, 1);
+  }
+
+  // deterministic per-camera sum of yobs[slot][9] over a CSR -> dst[9 nc] (+ all-reduce across shards)
+  int camera_reduce(const int* slots, const ReduceItem* items, int nitems, const int* item_ptr, S* dst, const int* done) {
+    k_cam_reduce<S><<<grid_for(nitems, 8, 8), 256, 0, stream>>>(D.yobs, slots, items, nitems, D.partial, done);
+    k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, item_ptr, nc, dst, done);
+    launches += 2;
+    return allreduce(dst, (size_t)9 * nc, false);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // ref: solver/linearizor_base.cpp:59-67
+  int compute_error(rba_residual_info* out) override {
+    int rc = start(ev_error); if (rc) return rc;
+    CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
+    k_error<S><<<EBLOCKS, 256, 0, stream>>>(D, ko, d_epart, d_flags);
+    k_sum_partials<6><<<1, 256, 0, stream>>>(d_epart, EBLOCKS, d_red);
+    launches += 2;
+    rc = allreduce(d_red, 6, true); if (rc) return rc;
+    rc = allreduce_flags(); if (rc) return rc;
+    CU(cudaMemcpyAsync(h_red, d_red, 6 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    rc = stop(ev_error); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    out->all_num_obs = (int64_t)llround(h_red[0]); out->all_error = h_red[1]; out->all_residual_sum = h_red[2];
+    out->valid_num_obs = (int64_t)llround(h_red[3]); out->valid_error = h_red[4]; out->valid_residual_sum = h_red[5];
+    out->is_numerically_valid = h_flags[0] ? 0 : 1;
+    out->pad_ = 0;
+    tm.residual_evaluation_time = elapsed(ev_error);
+    return RBA_OK;
+  }
+
+  // ref: solver/linearizor_qr.cpp:78-138 (staged: LinearizationQR::get_stage1, linearization_qr.hpp:634-712)
+  int linearize() override {
+    const long long l0 = launches;
+    int rc = start(ev_stage1); if (rc) return rc;
+    CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
+    // pass A: squared column norms of the weighted pose Jacobians -> pose_jacobian_scaling_
+    k_jp_norms<S><<<grid_for(L.nslots, 256, 8), 256, 0, stream>>>(D, ko, d_flags);
+    ++launches;
+    rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.diag2, nullptr); if (rc) return rc;
+    k_scaling<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.diag2, D.scaling, 9 * nc, (S)ko.jacobi_eps);
+    // pass B: linearize (scaled) + Jl scaling + Householder QR + panel write
+    k_linearize_qr<S><<<grid_for(D.ntiles, k1_warps, 4), k1_warps * 32, k1_smem, stream>>>(D, ko, L.k1_scratch_per_warp, d_flags);
+    launches += 2;
+    if (opt.preconditioner_type == 0) {
+      // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)
+      rc = precond_blocks(false, D.jblocks); if (rc) return rc;
+    }
+    rc = allreduce_flags(); if (rc) return rc;
+    CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    rc = stop(ev_stage1); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaGetLastError());
+    tm.stage1_time = elapsed(ev_stage1);
+    tm.kernel_launches = launches - l0;
+    linearized = true;
+    new_linearization_point = true;
+    damping_valid = false;
+    have_inc = false;
+    if (h_flags[0]) { linearized = false; return RBA_NUMERICAL_FAILURE; }  // reference: CHECK abort (linearizor_qr.cpp:121-122)
+    return RBA_OK;
+  }
+
+  int precond_blocks(bool schur, S* dst) {
+    k_precond_partial<S><<<(n_pb_items + 127) / 128, 128, 0, stream>>>(D.rec, d_csr_obs_slots, d_pb_items, n_pb_items, schur ? 1 : 0, D.pblk);
+    k_precond_final<S><<<(45 * nc + 255) / 256, 256, 0, stream>>>(D.pblk, d_pb_item_ptr, nc, dst);
+    launches += 2;
+    return allreduce(dst, (size_t)81 * nc, false);
+  }
+
+  // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
+  void matvec_launch(const S* xvec, const int* done) {
+    const int nitems = (int)L.items.size();
+    if (L.n_items_large > 0) {
+      k_matvec_large<S, K4_WARPS, KPMAX><<<grid_for(L.n_items_large, K4_WARPS, 4), K4_WARPS * 32, k4_smem_small, stream>>>(
+          D, d_items, 0, L.n_items_large, L.k4_scratch_per_warp, xvec, done);
+      ++launches;
+    }
+    if (nitems > L.n_items_large) {
+      k_matvec_small<S, K4_WARPS><<<grid_for(nitems - L.n_items_large, K4_WARPS, 5), K4_WARPS * 32, k4_smem_small, stream>>>(
+          D, d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done);
+      ++launches;
+    }
+    k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, done);
+    ++launches;
+    ++tm.matvec_launches;
+  }
+  // q_out = H vec = sum + lambda vec ; optional partial p.q
+  int matvec_finish(const S* vec, S* out, S lambda, PcgState* st, double* part) {
+    if (opt.nranks == 1) {
+      k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, D.partial, d_csr_y_item_ptr, nullptr, vec, out, lambda, part);
+      ++launches;
+    } else {
+      k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, d_csr_y_item_ptr, nc, D.y, st ? &st->done : nullptr);
+      int rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
+      k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, nullptr, nullptr, D.y, vec, out, lambda, part);
+      launches += 2;
+    }
+    return RBA_OK;
+  }
+
+  // ref: solver/linearizor_qr.cpp:140-265
+  int solve(double lambda_d, void* inc_out, rba_cg_summary* cg) override {
+    if (!linearized) { g_err = "rba_solve called before a successful rba_linearize"; return RBA_ERR_STATE; }
+    const S lambda = (S)lambda_d;
+    const long long l0 = launches;
+    tm.matvec_launches = 0;
+    int rc = start(ev_stage2); if (rc) return rc;
+    // stage 2: landmark damping + gradient (+ SCHUR_JACOBI blocks)
+    k_stage2<S><<<grid_for(D.ntiles, 4, 8), 128, 0, stream>>>(D, lambda);
+    ++launches;
+    rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b, nullptr); if (rc) return rc;
+    const bool schur = opt.preconditioner_type == 1;
+    if (schur) { rc = precond_blocks(true, D.blocks); if (rc) return rc; }
+    rc = stop(ev_stage2); if (rc) return rc;
+    rc = start(ev_precond); if (rc) return rc;
+    // pose damping lambda*I added to the blocks, then explicit inverse (ref: linearization_qr.hpp:796-802, linearizor_qr.cpp:228-237)
+    k_precond_invert<S><<<(nc + 63) / 64, 64, 0, stream>>>(schur ? D.blocks : D.jblocks, lambda, nc, schur ? D.blocks : nullptr, D.inv);
+    ++launches;
+    rc = stop(ev_precond); if (rc) return rc;
+    last_lambda = lambda;
+    damping_valid = true;
+    // PCG (ref: cg/conjugate_gradient.hpp:113-298 ; linearizor_base.cpp:81-103)
+    rc = start(ev_pcg); if (rc) return rc;
+    k_pcg_init<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part);
+    ++launches;
+    const int max_it = std::max(opt.max_linear_solver_iterations, 1);
+    const int period = opt.residual_reset_period;
+    const int chk = opt.pcg_check_period;
+    int i = 1;
+    int pending[2] = {0, 0};
+    int slot = 0;
+    bool finished = false;
+    while (i <= max_it && !finished) {
+      const int chunk_end = std::min(i + chk - 1, max_it);
+      for (; i <= chunk_end; ++i) {
+        k_pcg_begin<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part, i, opt.eta, opt.min_linear_solver_iterations, 0);
+        ++launches;
+        matvec_launch(D.p, &d_state->done);
+        rc = matvec_finish(D.p, D.q, lambda, d_state, d_part_pq); if (rc) return rc;
+        if (i % period == 0) {
+          k_pcg_update<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part_pq, d_part, i, 1);
+          ++launches;
+          matvec_launch(D.x, &d_state->done);
+          rc = matvec_finish(D.x, D.q, lambda, d_state, nullptr); if (rc) return rc;
+          k_pcg_update<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part_pq, d_part, i, 2);
+          ++launches;
+        } else {
+          k_pcg_update<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part_pq, d_part, i, 0);
+          ++launches;
+        }
+      }
+      CU(cudaMemcpyAsync(&h_state[slot], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+      CU(cudaEventRecord(poll_ev[slot], stream));
+      pending[slot] = 1;
+      const int other = slot ^ 1;
+      if (pending[other]) {
+        CU(cudaEventSynchronize(poll_ev[other]));
+        pending[other] = 0;
+        if (h_state[other].done) finished = true;
+      }
+      slot = other;
+    }
+    k_pcg_begin<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part, i, opt.eta, opt.min_linear_solver_iterations, 1);
+    ++launches;
+    CU(cudaMemcpyAsync(&h_state[0], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+    if (inc_out) CU(cudaMemcpyAsync(inc_out, D.inc, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    rc = stop(ev_pcg); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaGetLastError());
+    have_inc = true;
+    new_linearization_point = false;
+    tm.stage2_time = elapsed(ev_stage2);
+    tm.compute_preconditioner_time = elapsed(ev_precond);
+    tm.solve_reduced_system_time = elapsed(ev_pcg);
+    tm.kernel_launches = launches - l0;
+    if (cg) {
+      cg->termination_type = h_state[0].term;
+      cg->num_iterations = h_state[0].iter;
+      cg->reason = h_state[0].reason;
+      cg->num_matvecs = h_state[0].iter + h_state[0].iter / period;
+    }
+    return RBA_OK;
+  }
+
+  // ref: solver/linearizor_qr.cpp:267-291
+  int apply(const void* inc_host, void* l_diff_out, bool update_cameras) override {
+    if (!linearized || !damping_valid) { g_err = "rba_apply / rba_back_substitute need rba_linearize + rba_solve first"; return RBA_ERR_STATE; }
+    const long long l0 = launches;
+    if (inc_host) CU(cudaMemcpyAsync(D.inc, inc_host, (size_t)9 * nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+    else if (!have_inc) { g_err = "no device-resident increment"; return RBA_ERR_STATE; }
+    int rc = start(ev_backsub); if (rc) return rc;
+    CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
+    const int grid = std::min(grid_for(D.ntiles, 4, 8), EBLOCKS);
+    k_back_substitute<S><<<grid, 128, 0, stream>>>(D, D.inc, d_epart, d_flags);
+    k_sum_partials<1><<<1, 256, 0, stream>>>(d_epart, grid, d_red);
+    launches += 2;
+    rc = allreduce(d_red, 1, true); if (rc) return rc;
+    rc = allreduce_flags(); if (rc) return rc;
+    rc = stop(ev_backsub); if (rc) return rc;
+    rc = start(ev_update); if (rc) return rc;
+    if (update_cameras) {
+      // NOTE: the reference skips the camera update when l_diff is not finite (linearizor_qr.cpp:275-277); the LM loop
+      // then rejects the step and restores the backup, so updating unconditionally is equivalent for the caller.
+      k_camera_update<S><<<(nc + 127) / 128, 128, 0, stream>>>(D, D.inc);
+      ++launches;
+    }
+    rc = stop(ev_update); if (rc) return rc;
+    CU(cudaMemcpyAsync(h_red, d_red, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaGetLastError());
+    tm.back_substitution_time = elapsed(ev_backsub);
+    tm.update_cameras_time = elapsed(ev_update);
+    tm.kernel_launches = launches - l0;
+    S l = (S)h_red[0];
+    int ret = RBA_OK;
+    if (h_flags[0] || !std::isfinite((double)l)) { l = std::numeric_limits<S>::quiet_NaN(); ret = RBA_NUMERICAL_FAILURE; }
+    *(S*)l_diff_out = l;
+    return ret;
+  }
+
+  int get_timings(rba_stage_timings* out) const override { *out = tm; out->kernel_launches = launches; return RBA_OK; }
+  int get_stats(rba_workload_stats* out) const override {
+    std::memset(out, 0, sizeof(*out));
+    out->num_landmarks_local = L.nl_local;
+    out->num_observations_local = L.nobs_local;
+    out->sum_n2 = L.sum_n2;
+    out->max_n = L.max_n;
+    out->num_tiles = (int)L.tiles.size();
+    out->panel_scalars = L.panel_scalars;
+    out->panel_scalars_algorithmic = 18 * L.sum_n2;
+    out->device_bytes = (int64_t)device_bytes;
+    out->matvec_algorithmic_bytes = (18 * L.sum_n2 + 18 * L.nobs_local) * (int64_t)sizeof(S) + 4 * L.nobs_local;
+    out->landmark_begin = L.lm_begin;
+    out->landmark_end = L.lm_end;
+    out->num_matvec_items = (int)L.items.size();
+    return RBA_OK;
+  }
+
+  int get_scaling(void* scaling, void* diag2) override {
+    if (scaling) CU(cudaMemcpyAsync(scaling, D.scaling, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    if (diag2) CU(cudaMemcpyAsync(diag2, D.diag2, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return RBA_OK;
+  }
+  int get_rhs(void* b) override {
+    CU(cudaMemcpyAsync(b, D.b, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return RBA_OK;
+  }
+  int get_precond(void* inv, void* blocks) override {
+    if (inv) CU(cudaMemcpyAsync(inv, D.inv, (size_t)81 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    if (blocks) CU(cudaMemcpyAsync(blocks, D.blocks, (size_t)81 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return RBA_OK;
+  }
+  // ref: qr/linearization_qr.hpp:823-825
+  int right_multiply(const void* x, void* y) override {
+    if (!linearized || !damping_valid) { g_err = "rba_right_multiply needs rba_linearize + rba_solve first"; return RBA_ERR_STATE; }
+    CU(cudaMemcpyAsync(D.z, x, (size_t)9 * nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+    matvec_launch(D.z, nullptr);
+    int rc = matvec_finish(D.z, D.y, last_lambda, nullptr, nullptr); if (rc) return rc;
+    CU(cudaMemcpyAsync(y, D.y, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaGetLastError());
+    return RBA_OK;
+  }
+
+  int time_matvec(int reps, double* sec) override {
+    if (!linearized || !damping_valid) { g_err = "rba_time_matvec needs rba_linearize + rba_solve first"; return RBA_ERR_STATE; }
+    matvec_launch(D.p, nullptr);  // warm-up
+    int rc = start(ev_mv); if (rc) return rc;
+    for (int r = 0; r < reps; ++r) matvec_launch(D.p, nullptr);
+    rc = stop(ev_mv); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaGetLastError());
+    *sec = elapsed(ev_mv) / std::max(reps, 1);
+    tm.matvec_time = *sec;
+    return RBA_OK;
+  }
+
+  int timer_start() override { return start(ev_user); }
+  int timer_stop(double* sec) override {
+    int rc = stop(ev_user); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    *sec = elapsed(ev_user);
+    return RBA_OK;
+  }
+  void* stream_ptr() override { return (void*)stream; }
+  int synchronize() override { CU(cudaStreamSynchronize(stream)); return RBA_OK; }
+
+  // reference-layout view of one landmark block (see header)
+  int debug_get_block(int lm, void* out, int rows, int cols, void* jls_out) override {
+    if (lm < L.lm_begin || lm >= L.lm_end) { g_err = "landmark not in this shard"; return RBA_ERR_INVALID_ARGUMENT; }
+    const int sidx = L.sorted_of_lm[lm - L.lm_begin];
+    const TileInfo& T = L.tiles[L.tile_of_sorted[sidx]];
+    const int n = T.n, G = T.G, KP = T.KP, g = sidx - T.lm_base;
+    const int pad = (4 - (9 * n) % 4) % 4, lm_idx = 9 * n + pad, res_idx = lm_idx + 3;
+    if (rows != 2 * n + 3 || cols != res_idx + 1) { g_err = "block dims mismatch"; return RBA_ERR_INVALID_ARGUMENT; }
+    CU(cudaStreamSynchronize(stream));
+    std::vector<S> panel((size_t)2 * n * KP * 64), rec((size_t)48 * n), lmk(24);
+    const int slot0 = T.slot_base + g * n;
+    CU(cudaMemcpy(panel.data(), D.panel + T.panel_off, panel.size() * sizeof(S), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rec.data(), D.rec + (size_t)48 * slot0, rec.size() * sizeof(S), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(lmk.data(), D.lmk + (size_t)24 * sidx, 24 * sizeof(S), cudaMemcpyDeviceToHost));
+    S* o = (S*)out;
+    std::fill(o, o + (size_t)rows * cols, S(0));
+    for (int c = 0; c < 9 * n; ++c) {
+      const int i = c / 9, p = c % 9;
+      for (int m = 0; m < 3; ++m) o[(size_t)m * cols + c] = rec[(size_t)48 * i + 18 + 9 * m + p];  // damped Q1^T Jp
+      const int pr = c / 2, v = c % 2, k = pr / G, j = pr % G, lane = g * G + j;
+      for (int r = 0; r < 2 * n; ++r) o[(size_t)(3 + r) * cols + c] = panel[(((size_t)r * KP + k) * 32 + lane) * 2 + v];
+    }
+    o[0 * cols + lm_idx] = lmk[9]; o[0 * cols + lm_idx + 1] = lmk[10]; o[0 * cols + lm_idx + 2] = lmk[11];
+    o[1 * cols + lm_idx + 1] = lmk[12]; o[1 * cols + lm_idx + 2] = lmk[13]; o[2 * cols + lm_idx + 2] = lmk[14];
+    for (int m = 0; m < 3; ++m) o[(size_t)m * cols + res_idx] = lmk[15 + m];
+    if (jls_out) for (int d = 0; d < 3; ++d) ((S*)jls_out)[d] = lmk[18 + d];
+    return RBA_OK;
+  }
+};
+
+template <class S>
+int create_impl(const rba_problem_view* pv, const rba_solver_opts* o, rba_handle** out) {
+  if (!pv || !o || !out) { g_err = "null argument"; return RBA_ERR_INVALID_ARGUMENT; }
+  if (pv->num_cameras <= 0 || pv->num_landmarks <= 0 || !pv->lm_obs_offset || !pv->obs_cam_idx || !pv->obs_xy) {
+    g_err = "empty problem";
+    return RBA_ERR_INVALID_ARGUMENT;
+  }
+  auto* s = new Solver<S>();
+  s->scalar_size = sizeof(S);
+  int rc = s->init(pv, o);
+  if (rc != RBA_OK) { delete s; return rc; }
+  *out = s;
+  return RBA_OK;
+}
+
+}  // namespace rba
+
+extern "C" {
+
+int32_t rba_abi_version(void) { return RBA_ABI_VERSION; }
+const char* rba_last_error(void) { return rba::g_err.c_str(); }
+
+void rba_default_solver_opts(rba_solver_opts* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->use_householder_marginalization = 1;
+  o->use_valid_projections_only = 0;
+  o->robust_norm = 0;
+  o->huber_parameter = 1.0;
+  o->jacobi_scaling_epsilon = 0.0;
+  o->preconditioner_type = 1;
+  o->min_linear_solver_iterations = 0;
+  o->max_linear_solver_iterations = 500;
+  o->eta = 0.1;
+  o->residual_reset_period = 10;
+  o->device = -1;
+  o->rank = 0;
+  o->nranks = 1;
+  o->pcg_check_period = 4;
+  o->use_cuda_graphs = 0;
+}
+
+int32_t rba_create_f32(const rba_problem_view* p, const rba_solver_opts* o, rba_handle** out) { return rba::create_impl<float>(p, o, out); }
+int32_t rba_create_f64(const rba_problem_view* p, const rba_solver_opts* o, rba_handle** out) { return rba::create_impl<double>(p, o, out); }
+int32_t rba_destroy(rba_handle* h) { delete h; return RBA_OK; }
+int32_t rba_get_workload_stats(const rba_handle* h, rba_workload_stats* out) { return h->get_stats(out); }
+int32_t rba_scalar_size(const rba_handle* h) { return h->scalar_size; }
+
+int32_t rba_partition_landmarks(int32_t nl, const int64_t* off, int32_t nranks, int32_t* bounds) {
+  if (nl <= 0 || nranks <= 0 || !off || !bounds) return RBA_ERR_INVALID_ARGUMENT;
+  rba::partition_landmarks(nl, off, nranks, bounds);
+  return RBA_OK;
+}
+
+int32_t rba_set_state(rba_handle* h, const void* cams, const void* lms) { return h->set_state(cams, lms); }
+int32_t rba_get_state(rba_handle* h, void* cams, void* lms) { return h->get_state(cams, lms); }
+int32_t rba_backup(rba_handle* h) { return h->backup(); }
+int32_t rba_restore(rba_handle* h) { return h->restore(); }
+int32_t rba_compute_error(rba_handle* h, rba_residual_info* out) { return h->compute_error(out); }
+int32_t rba_linearize(rba_handle* h) { return h->linearize(); }
+
+#define CHECK_TYPE(h, sz) \
+  if ((h)->scalar_size != (sz)) { rba::g_err = "scalar type of the handle does not match the entry point"; return RBA_ERR_INVALID_ARGUMENT; }
+
+int32_t rba_solve_f32(rba_handle* h, float lambda, float* inc, rba_cg_summary* cg) { CHECK_TYPE(h, 4); return h->solve(lambda, inc, cg); }
+int32_t rba_solve_f64(rba_handle* h, double lambda, double* inc, rba_cg_summary* cg) { CHECK_TYPE(h, 8); return h->solve(lambda, inc, cg); }
+int32_t rba_apply_f32(rba_handle* h, const float* inc, float* l) { CHECK_TYPE(h, 4); return h->apply(inc, l, true); }
+int32_t rba_apply_f64(rba_handle* h, const double* inc, double* l) { CHECK_TYPE(h, 8); return h->apply(inc, l, true); }
+int32_t rba_back_substitute_f32(rba_handle* h, const float* inc, float* l) { CHECK_TYPE(h, 4); return h->apply(inc, l, false); }
+int32_t rba_back_substitute_f64(rba_handle* h, const double* inc, double* l) { CHECK_TYPE(h, 8); return h->apply(inc, l, false); }
+int32_t rba_get_timings(const rba_handle* h, rba_stage_timings* out) { return h->get_timings(out); }
+int32_t rba_get_jacobian_scaling(rba_handle* h, void* s, void* d) { return h->get_scaling(s, d); }
+int32_t rba_get_rhs(rba_handle* h, void* b) { return h->get_rhs(b); }
+int32_t rba_get_preconditioner(rba_handle* h, void* inv, void* blocks) { return h->get_precond(inv, blocks); }
+int32_t rba_right_multiply(rba_handle* h, const void* x, void* y) { return h->right_multiply(x, y); }
+int32_t rba_debug_get_block(rba_handle* h, int32_t lm, void* out, int32_t rows, int32_t cols, void* jls) {
+  return h->debug_get_block(lm, out, rows, cols, jls);
+}
+int32_t rba_time_matvec(rba_handle* h, int32_t reps, double* sec) { return h->time_matvec(reps, sec); }
+int32_t rba_timer_start(rba_handle* h) { return h->timer_start(); }
+int32_t rba_timer_stop(rba_handle* h, double* sec) { return h->timer_stop(sec); }
+void* rba_stream(rba_handle* h) { return h->stream_ptr(); }
+int32_t rba_synchronize(rba_handle* h) { return h->synchronize(); }
+
+int32_t rba_nccl_unique_id(void* out128) {
+  rba::NcclApi* api = rba::nccl_api();
+  if (!api) { rba::g_err = "libnccl.so.2 could not be loaded"; return RBA_ERR_NCCL; }
+  ncclUniqueId id;
+  ncclResult_t r = api->GetUniqueId(&id);
+  if (r != ncclSuccess) { rba::g_err = std::string("ncclGetUniqueId: ") + api->GetErrorString(r); return RBA_ERR_NCCL; }
+  std::memcpy(out128, &id, sizeof(id));
+  return RBA_OK;
+}
+int32_t rba_comm_init(rba_handle* h, const void* uid) { return h->comm_init(uid); }
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs.
+
+Tolerances (relative norm ||a-b||/(||a||+||b||), reference testing/eigen_utils.hpp:104-108):
+  single stage, identical inputs:   f32 5e-5 (1e-5 on the reference's fixture; see test_oracle_properties.py), f64 1e-11
+  after a PCG solve (inc, l_diff):  f32 2e-3, f64 1e-8   (error growth through PCG; CG iteration count +-2)
+  indices / counts:                 bit-exact
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL1 = {np.float32: 5e-5, np.float64: 1e-11}
+TOLS = {np.float32: 2e-3, np.float64: 1e-8}
+
+
+def make_pair(arrays, dtype, **opt_kw):
+    import rootba_b200 as rb
+    from oracle import oracle_py as orc
+    okw = {}
+    so = rb.SolverOptions()
+    if "preconditioner_type" in opt_kw:
+        so.preconditioner_type = opt_kw["preconditioner_type"]
+        okw["preconditioner_type"] = {"JACOBI": 0, "SCHUR_JACOBI": 1}[so.preconditioner_type]
+    if "robust_norm" in opt_kw:
+        so.residual.robust_norm = opt_kw["robust_norm"]
+        so.residual.huber_parameter = opt_kw.get("huber_parameter", 1.0)
+        okw["robust_norm"] = 1 if so.residual.robust_norm == "HUBER" else 0
+        okw["huber_parameter"] = so.residual.huber_parameter
+    if "optimized_cost" in opt_kw:
+        so.optimized_cost = opt_kw["optimized_cost"]
+        okw["optimized_cost"] = {"ERROR": 0, "ERROR_VALID": 1, "ERROR_VALID_AVG": 2}[so.optimized_cost]
+        okw["use_valid_projections_only"] = int(so.use_projection_validity_check())
+    if "max_num_iterations" in opt_kw:
+        so.max_num_iterations = okw["max_num_iterations"] = opt_kw["max_num_iterations"]
+    bp = rb.BalProblem.from_arrays(arrays, dtype)
+    lin = rb.LinearizorQR.create(bp, so)
+    o = orc.Oracle(arrays, dtype, orc.default_options(num_threads=0, **okw))
+    return bp, lin, o, so
+
+
+@pytest.fixture(scope="module")
+def mixed_problem():
+    """small problem with a wide range of track lengths (covers every group-size class incl. row chunks)"""
+    from rootba_b200.synthetic import synth_bal
+    return synth_bal(150, 1500, 9.0, seed=11, max_track=150)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_compute_error(small_problem, dtype):
+    bp, lin, o, _ = make_pair(small_problem, dtype)
+    g, c = lin.compute_error(), o.compute_error()
+    assert g["all"]["num_obs"] == c["all"]["num_obs"] == small_problem.nobs
+    assert g["valid"]["num_obs"] == c["valid"]["num_obs"]
+    assert g["is_numerically_valid"] and c["is_numerically_valid"]
+    tol = 1e-5 if dtype == np.float32 else 1e-12
+    assert abs(g["all"]["error"] - c["all"]["error"]) <= tol * c["all"]["error"]
+    assert abs(g["all"]["residual_sum"] - c["all"]["residual_sum"]) <= tol * c["all"]["residual_sum"]
+    lin.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("which", ["small", "mixed"])
+def test_stage_parity(small_problem, mixed_problem, dtype, which):
+    arrays = small_problem if which == "small" else mixed_problem
+    bp, lin, o, _ = make_pair(arrays, dtype)
+    tol = TOL1[dtype]
+    lam = 0.1
+    lin.linearize()
+    assert o.linearize()
+    s_g, d_g = lin.get_jacobian_scaling()
+    assert rel_err(s_g, o.get_scaling()) < tol
+    # solve on both (stage 2 + preconditioner + PCG)
+    inc_g = lin.solve(lam)
+    inc_c, dbg = o.solve(lam, want_debug=True)
+    assert rel_err(lin.get_rhs(), dbg["b"]) < tol * 4
+    inv_g, blk_g = lin.get_preconditioner()
+    worst = max(rel_err(inv_g[c], dbg["inv_blocks"][c]) for c in range(lin.nc))
+    assert worst < (5e-3 if dtype == np.float32 else 1e-8), worst
+    # blocks in the reference storage layout: Q1 rows, R, Q1^T r, Q2 panel incl. damping rows
+    n_all = arrays.track_lengths()
+    picks = sorted(set([int(np.argmax(n_all)), int(np.argmin(n_all)), 0, arrays.nl - 1] +
+                       [int(np.nonzero(n_all == k)[0][0]) for k in np.unique(n_all)[:12]]))
+    for lm in picks:
+        bg, lm_idx, res_idx, jls_g = lin.debug_get_block(lm)
+        bc, li, ri, jls_c = o.get_block(lm)
+        assert (li, ri) == (lm_idx, res_idx) and bg.shape == bc.shape
+        n = n_all[lm]
+        assert rel_err(jls_g, jls_c) < tol
+        assert rel_err(bg[:3, :9 * n], bc[:3, :9 * n]) < tol * 4, lm
+        assert rel_err(np.triu(bg[:3, lm_idx:lm_idx + 3]), np.triu(bc[:3, lm_idx:lm_idx + 3])) < tol * 4, lm
+        assert rel_err(bg[:3, res_idx], bc[:3, res_idx]) < tol * 4, lm
+        assert rel_err(bg[3:, :9 * n], bc[3:, :9 * n]) < tol * 4, (lm, n)
+    # operator
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, 9 * lin.nc).astype(dtype)
+    assert rel_err(lin.right_multiply(x), o.right_multiply(x)) < tol * 4
+    # PCG result
+    assert abs(lin.last_cg.num_iterations - dbg["cg_iterations"]) <= 2
+    assert lin.last_cg.termination_type == dbg["cg_termination"]
+    assert rel_err(inc_g, inc_c) < TOLS[dtype]
+    # back substitution with the SAME increment on both sides
+    pose_inc = (rng.uniform(-1, 1, 9 * lin.nc) * 0.01).astype(dtype)
+    l_g = lin.back_substitute(pose_inc)
+    l_c, ok = o.back_substitute(pose_inc)
+    assert ok and abs(l_g - l_c) <= tol * 20 * abs(l_c)
+    lin.download_state()
+    _, lms_c = o.get_state()
+    assert rel_err(bp.lms, lms_c) < tol
+    lin.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_apply_camera_update(small_problem, dtype):
+    bp, lin, o, _ = make_pair(small_problem, dtype)
+    lin.linearize(); assert o.linearize()
+    lin.solve(1e-4); o.solve(1e-4)
+    rng = np.random.default_rng(5)
+    inc = (rng.uniform(-1, 1, 9 * lin.nc) * 0.05).astype(dtype)
+    l_g = lin.apply(inc.copy())
+    l_c = o.apply(inc.copy())
+    assert abs(l_g - l_c) <= TOL1[dtype] * 20 * abs(l_c)
+    lin.download_state()
+    cams_c, lms_c = o.get_state()
+    assert rel_err(bp.cams, cams_c) < (1e-6 if dtype == np.float32 else 1e-13)
+    assert rel_err(bp.lms, lms_c) < TOL1[dtype]
+    lin.close()
+
+
+def test_backup_restore(small_problem):
+    bp, lin, o, _ = make_pair(small_problem, np.float64)
+    cams0, lms0 = bp.cams.copy(), bp.lms.copy()
+    lin.linearize()
+    inc = lin.solve(1e-4)
+    bp.backup()
+    lin.apply(inc)
+    lin.download_state()
+    assert not np.array_equal(bp.lms, lms0)
+    bp.restore()
+    lin.download_state()
+    assert np.array_equal(bp.lms, lms0) and np.array_equal(bp.cams, cams0)
+    lin.close()
+
+
+@pytest.mark.parametrize("dtype,kw", [
+    (np.float64, {}),
+    (np.float32, {}),
+    (np.float64, {"preconditioner_type": "JACOBI"}),
+    (np.float32, {"robust_norm": "HUBER", "huber_parameter": 2.0}),
+    (np.float64, {"optimized_cost": "ERROR_VALID"}),
+])
+def test_lm_trajectory(small_problem, dtype, kw):
+    import rootba_b200 as rb
+    bp, lin, o, so = make_pair(small_problem, dtype, max_num_iterations=6, **kw)
+    summ = rb.bundle_adjust_manual(bp, so, linearizor=lin)
+    rows, term = o.optimize()
+    g_it = summ["iterations"]
+    assert len(g_it) == len(rows)
+    tol = 1e-4 if dtype == np.float32 else 1e-9
+    for a, b in zip(g_it, rows):
+        assert a["iteration"] == int(b["iteration"])
+        assert bool(a["step_is_successful"]) == bool(b["step_is_successful"])
+        ca = a["cost"]["all"]["error"]
+        assert abs(ca - b["cost"]) <= tol * b["cost"], (a["iteration"], ca, b["cost"])
+        if a["iteration"] > 0:
+            assert abs(a["linear_solver_iterations"] - int(b["cg_iterations"])) <= 2
+    assert g_it[-1]["cost"]["all"]["error"] < 0.2 * g_it[0]["cost"]["all"]["error"]
+    lin.close()
+
+
+def test_long_tracks_generic_path():
+    """track lengths beyond the register-resident classes (KP > 16) take the shared-memory matvec variant"""
+    from rootba_b200.synthetic import synth_bal
+    arrays = synth_bal(300, 120, 60.0, seed=4, max_track=300)
+    assert arrays.track_lengths().max() > 113
+    for dtype in (np.float32, np.float64):
+        bp, lin, o, _ = make_pair(arrays, dtype)
+        lin.linearize(); assert o.linearize()
+        inc_g = lin.solve(0.01)
+        inc_c, _ = o.solve(0.01)
+        x = np.random.default_rng(0).uniform(-1, 1, 9 * lin.nc).astype(dtype)
+        assert rel_err(lin.right_multiply(x), o.right_multiply(x)) < TOL1[dtype] * 4
+        assert rel_err(inc_g, inc_c) < TOLS[dtype]
+        lin.close()
+
+
+def test_minimal_tracks_and_ragged_tiles():
+    """n = 2 only, landmark count not a multiple of the tile width"""
+    from rootba_b200.synthetic import synth_bal
+    arrays = synth_bal(9, 77, 2.0001, seed=2)
+    assert arrays.track_lengths().max() <= 3
+    bp, lin, o, _ = make_pair(arrays, np.float64)
+    lin.linearize(); assert o.linearize()
+    inc_g = lin.solve(1e-3); inc_c, _ = o.solve(1e-3)
+    assert rel_err(inc_g, inc_c) < 1e-8
+    lin.close()
+
+
+def test_rejects_bad_input(small_problem):
+    import rootba_b200 as rb
+    a = small_problem
+    # a landmark with a single observation: the reference LOG(FATAL)s (ipp:73-76); we return an error
+    off = a.lm_off.copy()
+    off[1] = off[0] + 1
+    bp = rb.BalProblem(a.cams, a.lms, off, a.obs_cam, a.obs_xy)
+    with pytest.raises(rb.RbaError):
+        rb.LinearizorQR.create(bp, rb.SolverOptions())
+    # solve before linearize is a protocol violation
+    bp2 = rb.BalProblem.from_arrays(a)
+    lin = rb.LinearizorQR.create(bp2, rb.SolverOptions())
+    with pytest.raises(rb.RbaError):
+        lin.solve(1e-4)
+    lin.close()
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] shape (ladybug-1723-156502, float32): size-independent properties"""
+    import rootba_b200 as rb
+    from rootba_b200.synthetic import synth_config
+    arrays = synth_config("ladybug-1723")
+    bp = rb.BalProblem.from_arrays(arrays, np.float32)
+    so = rb.SolverOptions(use_double=False, max_num_iterations=3)
+    lin = rb.LinearizorQR.create(bp, so)
+    st = lin.stats()
+    n = arrays.track_lengths()
+    assert st["sum_n2"] == int((n * n).sum()) and st["num_observations_local"] == arrays.nobs  # bit-exact indexing
+    e0 = lin.compute_error()
+    assert e0["all"]["num_obs"] == arrays.nobs and e0["is_numerically_valid"]
+    lin.linearize()
+    lin.solve(1e-4)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, 9 * lin.nc).astype(np.float32)
+    y = rng.uniform(-1, 1, 9 * lin.nc).astype(np.float32)
+    Hx, Hy = lin.right_multiply(x).astype(np.float64), lin.right_multiply(y).astype(np.float64)
+    # symmetry, positive definiteness, linearity of the RCS operator
+    assert abs(y @ Hx - x @ Hy) <= 1e-4 * (abs(y @ Hx) + abs(x @ Hy))
+    assert x @ Hx > 0
+    Hxy = lin.right_multiply((x + 2 * y).astype(np.float32)).astype(np.float64)
+    assert rel_err(Hxy, Hx + 2 * Hy) < 1e-4
+    # two runs of the deterministic scatter give bit-identical results
+    assert np.array_equal(lin.right_multiply(x), lin.right_multiply(x))
+    summ = rb.bundle_adjust_manual(bp, so, linearizor=lin)
+    costs = [it["cost"]["all"]["error"] for it in summ["iterations"] if it.get("step_is_successful")]
+    assert costs[-1] < 0.5 * costs[0]
+    lin.close()
