@@ -66,8 +66,9 @@ class BalProblem:
 
     def __init__(self, cams, lms, lm_off, obs_cam, obs_xy, dtype=np.float64):
         self.dtype = np.dtype(dtype)
-        self.cams = np.ascontiguousarray(cams, dtype=self.dtype).reshape(-1, 10)
-        self.lms = np.ascontiguousarray(lms, dtype=self.dtype).reshape(-1, 3)
+        # the problem owns its optimisation state (it is updated in place by the solver)
+        self.cams = np.array(cams, dtype=self.dtype, order="C", copy=True).reshape(-1, 10)
+        self.lms = np.array(lms, dtype=self.dtype, order="C", copy=True).reshape(-1, 3)
         self.lm_off = np.ascontiguousarray(lm_off, dtype=np.int64)
         self.obs_cam = np.ascontiguousarray(obs_cam, dtype=np.int32)
         self.obs_xy = np.ascontiguousarray(obs_xy, dtype=self.dtype).reshape(-1, 2)
