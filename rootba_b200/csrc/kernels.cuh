@@ -793,6 +793,40 @@ __global__ void __launch_bounds__(64) k_precond_invert(const S* __restrict__ src
 //   2-scalar vector loads; row dot products are reduced with log2(G) shuffles; x is gathered and y is
 //   written through a per-warp shared-memory transpose so that both are coalesced.
 // ------------------------------------------------------------------------------------------------
+// Gather x_red of the W landmarks of a tile into shared memory (xs[g][c], row stride CS, padding zeroed).
+// All index loads are issued before the first dependent x load, and all x loads before the first store, so a
+// tile costs two memory round trips instead of 2 * (columns / 32).
+template <class S, int KP>
+__device__ __forceinline__ void gather_x(const DevPtrs<S>& D, const TileInfo& T, int lane, S* xs,
+                                         const S* __restrict__ xvec, int CS) {
+  constexpr int NT = 2 * KP;  // W * ncols <= 64 * KP
+  const int n = T.n, W = 32 / T.G, ncols = 9 * n;
+  const int total = T.nvalid * ncols;
+  for (int e = lane; e < W * CS; e += 32) xs[e] = 0;
+  int off[NT], dst[NT];
+  {
+    int g2 = 0, c = lane;
+    while (c >= ncols) { c -= ncols; ++g2; }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int e = lane + 32 * t;
+      const bool ok = e < total;
+      const int i = c / 9, p = c - 9 * i;
+      off[t] = ok ? D.slot_cam[T.slot_base + g2 * n + i] * 9 + p : -1;
+      dst[t] = g2 * CS + c;
+      c += 32;
+      while (c >= ncols) { c -= ncols; ++g2; }
+    }
+  }
+  S val[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) val[t] = off[t] >= 0 ? xvec[off[t]] : S(0);
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < NT; ++t) if (off[t] >= 0) xs[dst[t]] = val[t];
+  __syncwarp();
+}
+
 template <class S, int KP>
 __device__ __forceinline__ void matvec_item(const DevPtrs<S>& D, const MatvecItem& it, const TileInfo& T, int lane,
                                             S* xs, const S* __restrict__ xvec) {
@@ -802,20 +836,7 @@ __device__ __forceinline__ void matvec_item(const DevPtrs<S>& D, const MatvecIte
   const int ncols = 9 * n;
   const int CS = (2 * G * KP) | 1;
   // zero padding columns, gather x_red of the W landmarks (coalesced runs of 9)
-  for (int e = lane; e < W * CS; e += 32) xs[e] = 0;
-  __syncwarp();
-  {
-    int g2 = 0, c = lane;
-    while (c >= ncols) { c -= ncols; ++g2; }
-    while (g2 < T.nvalid) {
-      const int i = c / 9, p = c - 9 * i;
-      const int cam = D.slot_cam[T.slot_base + g2 * n + i];
-      xs[g2 * CS + c] = xvec[9 * (size_t)cam + p];
-      c += 32;
-      while (c >= ncols) { c -= ncols; ++g2; }
-    }
-  }
-  __syncwarp();
+  gather_x<S, KP>(D, T, lane, xs, xvec, CS);
   V2 xv[KP], yv[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
@@ -894,6 +915,219 @@ __device__ __forceinline__ void matvec_item_generic(const DevPtrs<S>& D, const M
   __syncwarp();
   for (int c = lane; c < ncols; c += 32) D.yobs[9 * (size_t)it.yslot_base + c] = ys[c];
   __syncwarp();
+}
+
+// ---- TMA (cp.async.bulk) + mbarrier helpers: 1-D bulk global->shared copies, SASS UBLKCP -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+// Producer cursor of the per-warp panel stream: the MatvecItems of a warp are consumed in order and every item
+// is one CONTIGUOUS chunk of HBM (nrows x KP x 64 scalars), cut into stages of <= STAGE_BYTES whole rows.
+template <class S>
+struct PanelStream {
+  const S* src;          // next global address to fetch
+  int rows_left;         // rows of the current producer item not yet requested
+  int row_scalars;       // KP * 64
+  int rows_per_stage;
+  int next_item;         // next item index of this warp's sequence to open
+  unsigned issued;       // stages issued so far
+};
+
+template <class S, int NS, int STAGE_BYTES>
+__device__ __forceinline__ bool stream_produce(PanelStream<S>& ps, const DevPtrs<S>& D, const MatvecItem* __restrict__ items,
+                                               int item_end, int item_stride, unsigned char* ring, uint64_t* bars, int lane) {
+  if (ps.rows_left == 0) {
+    if (ps.next_item >= item_end) return false;
+    const MatvecItem it = items[ps.next_item];
+    const TileInfo T = D.tiles[it.tile];
+    ps.row_scalars = T.KP * 64;
+    ps.src = D.panel + T.panel_off + (size_t)it.row0 * ps.row_scalars;
+    ps.rows_left = it.nrows;
+    ps.rows_per_stage = max(1, STAGE_BYTES / (int)(ps.row_scalars * sizeof(S)));
+    ps.next_item += item_stride;
+  }
+  const int rows = min(ps.rows_per_stage, ps.rows_left);
+  const uint32_t bytes = (uint32_t)(rows * ps.row_scalars * sizeof(S));
+  const unsigned slot = ps.issued % NS;
+  if (lane == 0) {
+    mbar_expect_tx(&bars[slot], bytes);
+    bulk_g2s(ring + (size_t)slot * STAGE_BYTES, ps.src, bytes, &bars[slot]);
+  }
+  ps.src += (size_t)rows * ps.row_scalars;
+  ps.rows_left -= rows;
+  ++ps.issued;
+  return true;
+}
+
+// predicated butterfly inside a group of G lanes (G uniform in the warp): no loop, no divergent branch
+template <class T>
+__device__ __forceinline__ T group_sum_p(T v, int G) {
+  T t;
+  t = __shfl_xor_sync(0xffffffffu, v, 16); if (G > 16) v += t;
+  t = __shfl_xor_sync(0xffffffffu, v, 8);  if (G > 8) v += t;
+  t = __shfl_xor_sync(0xffffffffu, v, 4);  if (G > 4) v += t;
+  t = __shfl_xor_sync(0xffffffffu, v, 2);  if (G > 2) v += t;
+  t = __shfl_xor_sync(0xffffffffu, v, 1);  if (G > 1) v += t;
+  return v;
+}
+
+// one item, rows streamed through the shared-memory ring filled by TMA bulk copies.
+// Every lane gathers x for the 2*KP columns it owns straight from the (L1/L2 resident) camera vector and
+// writes its y entries straight to the per-observation buffer: no transposition, no per-item barrier.
+template <class S, int KP, int NS, int STAGE_BYTES>
+__device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const MatvecItem& it, const TileInfo& T, int lane,
+                                                const S* __restrict__ xvec, PanelStream<S>& ps, unsigned& consumed,
+                                                const MatvecItem* __restrict__ items, int item_end, int item_stride,
+                                                unsigned char* ring, uint64_t* bars) {
+  using V2 = typename ST<S>::V2;
+  const int n = T.n, G = T.G;
+  const int g = lane / G, j = lane - g * G;
+  const int ncols = 9 * n;
+  const bool active = g < T.nvalid;
+  const int slot0 = T.slot_base + g * n;
+  // ---- gather: offsets first (index loads), then the x loads ----
+  int off0[KP], off1[KP];
+  {
+    const int step = 2 * G;
+    const int di = step / 9, dp = step - 9 * di;
+    int c = 2 * j;
+    int i = c / 9, p = c - 9 * i;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const bool v0 = active && c < ncols, v1 = active && (c + 1) < ncols;
+      const int i1 = (p == 8) ? i + 1 : i, p1 = (p == 8) ? 0 : p + 1;
+      const int cam0 = v0 ? __ldg(D.slot_cam + slot0 + i) : 0;
+      const int cam1 = v1 ? __ldg(D.slot_cam + slot0 + i1) : 0;
+      off0[k] = v0 ? 9 * cam0 + p : -1;
+      off1[k] = v1 ? 9 * cam1 + p1 : -1;
+      c += step; i += di; p += dp;
+      if (p >= 9) { p -= 9; ++i; }
+    }
+  }
+  V2 xv[KP], yv[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    xv[k] = mk2(off0[k] >= 0 ? __ldg(xvec + off0[k]) : S(0), off1[k] >= 0 ? __ldg(xvec + off1[k]) : S(0));
+    yv[k] = mk2(S(0), S(0));
+  }
+  // ---- rows from the ring ----
+  int rows_left = it.nrows;
+  constexpr int RPS = (STAGE_BYTES / (int)(KP * 64 * sizeof(S))) > 0 ? (STAGE_BYTES / (int)(KP * 64 * sizeof(S))) : 1;
+  while (rows_left > 0) {
+    const unsigned slot = consumed % NS;
+    mbar_wait(&bars[slot], (consumed / NS) & 1u);
+    const int rows = min(RPS, rows_left);
+    const V2* st = reinterpret_cast<const V2*>(ring + (size_t)slot * STAGE_BYTES) + lane;
+    int r = 0;
+    for (; r + 2 <= rows; r += 2) {  // two rows at a time: independent dependency chains
+      V2 va[KP], vb[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) { va[k] = st[(r * KP + k) * 32]; vb[k] = st[((r + 1) * KP + k) * 32]; }
+      S da0 = 0, da1 = 0, db0 = 0, db1 = 0;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        da0 = fma(va[k].x, xv[k].x, da0); da1 = fma(va[k].y, xv[k].y, da1);
+        db0 = fma(vb[k].x, xv[k].x, db0); db1 = fma(vb[k].y, xv[k].y, db1);
+      }
+      S da = da0 + da1, db = db0 + db1;
+      da = group_sum_p(da, G); db = group_sum_p(db, G);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        yv[k].x = fma(da, va[k].x, yv[k].x); yv[k].y = fma(da, va[k].y, yv[k].y);
+        yv[k].x = fma(db, vb[k].x, yv[k].x); yv[k].y = fma(db, vb[k].y, yv[k].y);
+      }
+    }
+    if (r < rows) {
+      V2 va[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) va[k] = st[(r * KP + k) * 32];
+      S da0 = 0, da1 = 0;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) { da0 = fma(va[k].x, xv[k].x, da0); da1 = fma(va[k].y, xv[k].y, da1); }
+      S da = group_sum_p(da0 + da1, G);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) { yv[k].x = fma(da, va[k].x, yv[k].x); yv[k].y = fma(da, va[k].y, yv[k].y); }
+    }
+    __syncwarp();  // every lane is done reading the stage before it is handed back to the TMA engine
+    ++consumed;
+    rows_left -= rows;
+    stream_produce<S, NS, STAGE_BYTES>(ps, D, items, item_end, item_stride, ring, bars, lane);
+  }
+  // ---- y: each lane writes the columns it owns (contiguous inside a group) ----
+  if (active) {
+    S* yo = D.yobs + 9 * (size_t)(it.yslot_base + g * n);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int c = 2 * j + 2 * G * k;
+      if (c < ncols) yo[c] = yv[k].x;
+      if (c + 1 < ncols) yo[c + 1] = yv[k].y;
+    }
+  }
+}
+
+// K4 (TMA variant): persistent warps, each streams the panels of its items through a private NS-stage
+// shared-memory ring (cp.async.bulk + mbarrier complete_tx), so the bytes in flight per SM are set by the
+// ring size (WARPS * NS * STAGE_BYTES) instead of by registers.
+template <class S, int WARPS, int NS, int STAGE_BYTES>
+__global__ void __launch_bounds__(WARPS * 32) k_matvec_small_tma(DevPtrs<S> D, const MatvecItem* __restrict__ items,
+                                                                  int item_begin, int item_end, int scratch_per_warp,
+                                                                  const S* __restrict__ xvec, const int* done) {
+  if (done && *done) return;
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  __shared__ __align__(8) uint64_t bars_all[WARPS][NS];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* ring = smem_tma + (size_t)wib * NS * STAGE_BYTES;
+  uint64_t* bars = bars_all[wib];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const int stride = gridDim.x * WARPS;
+  const int first = item_begin + blockIdx.x * WARPS + wib;
+  PanelStream<S> ps;
+  ps.src = nullptr; ps.rows_left = 0; ps.row_scalars = 0; ps.rows_per_stage = 1; ps.next_item = first; ps.issued = 0;
+  unsigned consumed = 0;
+#pragma unroll 1
+  for (int s = 0; s < NS; ++s)
+    if (!stream_produce<S, NS, STAGE_BYTES>(ps, D, items, item_end, stride, ring, bars, lane)) break;
+  for (int q = first; q < item_end; q += stride) {
+    const MatvecItem it = items[q];
+    const TileInfo T = D.tiles[it.tile];
+    switch (T.KP) {
+      case 5: matvec_item_tma<S, 5, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
+      case 6: matvec_item_tma<S, 6, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
+      case 7: matvec_item_tma<S, 7, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
+      case 8: matvec_item_tma<S, 8, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
+      case 9: matvec_item_tma<S, 9, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
+      default: break;
+    }
+  }
 }
 
 template <class S, int WARPS>

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -247,12 +248,27 @@ struct Solver : rba_handle {
     if (k4_smem_small > 200 * 1024) { g_err = "matvec scratch exceeds shared memory"; return RBA_ERR_UNSUPPORTED; }
     CU(cudaFuncSetAttribute(k_matvec_small<S, K4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k4_smem_small, 1024)));
     CU(cudaFuncSetAttribute((k_matvec_large<S, K4_WARPS, KPMAX>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k4_smem_small, 1024)));
+    {
+      const char* e = getenv("RBA_MATVEC");
+      use_tma = !(e && std::string(e) == "ldg");
+      k4_smem_tma = (size_t)K4_WARPS * K4_NS * K4_STAGE;
+      if (k4_smem_tma > 220 * 1024) use_tma = false;
+      if (use_tma) {
+        CU(cudaFuncSetAttribute((k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_tma));
+        k4_tma_blocks_per_sm = std::max(1, (int)((220 * 1024) / (k4_smem_tma + 1024)));
+        if (const char* b = getenv("RBA_MATVEC_BLOCKS_PER_SM")) k4_tma_blocks_per_sm = std::max(1, atoi(b));
+      }
+    }
     CU(cudaStreamSynchronize(stream));
     return RBA_OK;
   }
   static constexpr int K4_WARPS = 4;
+  static constexpr int K4_NS = 3;             // TMA ring stages per warp
+  static constexpr int K4_STAGE = 4608;       // bytes per stage (2 rows of an f32 KP=9 tile)
   int k1_warps = 4;
-  size_t k1_smem = 0, k4_smem_small = 0;
+  size_t k1_smem = 0, k4_smem_small = 0, k4_smem_tma = 0;
+  bool use_tma = true;
+  int k4_tma_blocks_per_sm = 2;
 
   // ------------------------------------------------------------------------------------------
   int allreduce(void* buf, size_t count, bool is_double) {
@@ -389,8 +405,12 @@ struct Solver : rba_handle {
       ++launches;
     }
     if (nitems > L.n_items_large) {
-      k_matvec_small<S, K4_WARPS><<<grid_for(nitems - L.n_items_large, K4_WARPS, 5), K4_WARPS * 32, k4_smem_small, stream>>>(
-          D, d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done);
+      if (use_tma)
+        k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE><<<grid_for(nitems - L.n_items_large, K4_WARPS, k4_tma_blocks_per_sm), K4_WARPS * 32, k4_smem_tma, stream>>>(
+            D, d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done);
+      else
+        k_matvec_small<S, K4_WARPS><<<grid_for(nitems - L.n_items_large, K4_WARPS, 5), K4_WARPS * 32, k4_smem_small, stream>>>(
+            D, d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done);
       ++launches;
     }
     k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, done);
