@@ -3,6 +3,7 @@
 // "ref:" citations are relative to /root/reference/src/rootba/.
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cfloat>
@@ -190,6 +191,21 @@ __device__ __forceinline__ void block_sum_store(double (&v)[K], double* out) {
   __syncthreads();
 }
 
+// block-wide sum of one double -> out[blockIdx.x*4 + k] (thread 0)
+__device__ __forceinline__ void block_sum_store4(double v, double* out, int k) {
+  __shared__ double sm4[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) sm4[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int q = 0; q < nw; ++q) s += sm4[q];
+    out[blockIdx.x * 4 + k] = s;
+  }
+  __syncthreads();
+}
+
 // sum of n <= 1024 partial doubles in a fixed order, result broadcast to every thread of the block
 __device__ __forceinline__ double block_sum_partials(const double* part, int n, int stride, int off) {
   __shared__ double bs_sm[32];
@@ -299,32 +315,50 @@ __global__ void __launch_bounds__(256) k_jp_norms(DevPtrs<S> D, KOpts o, int* ba
 // deterministic scatter, phase 2: per-camera segmented sum of 9-vectors
 //   warp per ReduceItem (segment of a camera's slot list) -> partial[item][9]
 // ------------------------------------------------------------------------------------------------
+// one warp reduces one ReduceItem (<= SEG_LEN slots).  Lane (s, c) = (lane / 9, lane % 9), s < 3, reads component c of
+// slot 3t + s: the 9 scalars of a slot are one 36-byte run, so a warp-wide load touches 3 slots = 3..6 sectors instead
+// of 32.  The slot indices are first staged in shared memory with coalesced loads (one round trip), then the value loads
+// are issued 16 deep, so an item costs ~1 + SEG_LEN/48 round trips instead of 2 * SEG_LEN/32.
+template <class S>
+__device__ __forceinline__ void cam_reduce_item(const S* __restrict__ src, const int* __restrict__ slots, const ReduceItem& I,
+                                                int lane, S* __restrict__ out9, int* sidx /* [SEG_LEN] per warp */) {
+  const int cnt = I.end - I.begin;
+#pragma unroll
+  for (int t = 0; t < SEG_LEN / 32; ++t) {
+    const int e = lane + 32 * t;
+    if (e < cnt) sidx[e] = __ldg(slots + I.begin + e);
+  }
+  __syncwarp();
+  const int s3 = lane / 9, c = lane - 9 * s3;
+  const bool on = lane < 27;
+  S acc = 0;
+  for (int base = 0; base < cnt; base += 48) {
+    S v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int e = base + 3 * t + s3;
+      v[t] = (on && e < cnt) ? src[9 * (size_t)sidx[e] + c] : S(0);
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc += v[t];
+  }
+  __syncwarp();
+  // lanes c, c + 9, c + 18 hold the three partial sums of component c
+  const S a1 = __shfl_sync(0xffffffffu, acc, (lane + 9) & 31);
+  const S a2 = __shfl_sync(0xffffffffu, acc, (lane + 18) & 31);
+  if (lane < 9) out9[lane] = acc + a1 + a2;
+}
+
 template <class S>
 __global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, const int* __restrict__ slots,
                                                      const ReduceItem* __restrict__ items, int nitems,
                                                      S* __restrict__ partial, const int* done) {
   if (done && *done) return;
+  __shared__ int sidx_all[8][SEG_LEN];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb) {
-    const ReduceItem I = items[it];
-    S acc[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) acc[c] = 0;
-    for (int e = I.begin + lane; e < I.end; e += 32) {
-      const S* v = src + 9 * (size_t)slots[e];
-#pragma unroll
-      for (int c = 0; c < 9; ++c) acc[c] += v[c];
-    }
-#pragma unroll
-    for (int c = 0; c < 9; ++c) acc[c] = warp_sum(acc[c]);
-    if (lane < 9) {
-      S v = acc[0];
-#pragma unroll
-      for (int c = 1; c < 9; ++c) if (lane == c) v = acc[c];
-      partial[9 * (size_t)it + lane] = v;
-    }
-  }
+  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb)
+    cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
 }
 
 // out[cam*9+c] = sum over the camera's items (fixed order)
@@ -769,7 +803,7 @@ __global__ void __launch_bounds__(64) k_precond_invert(const S* __restrict__ src
       L[9 * i + jj] = t / d;
     }
   }
-  S* out = inv + 81 * (size_t)cam;
+  // A is no longer needed: reuse it for the inverse
 #pragma unroll 1
   for (int col = 0; col < 9; ++col) {
     S yv[9];
@@ -780,10 +814,12 @@ __global__ void __launch_bounds__(64) k_precond_invert(const S* __restrict__ src
     }
     for (int i = 8; i >= 0; --i) {
       S t = yv[i];
-      for (int k = i + 1; k < 9; ++k) t -= L[9 * k + i] * out[9 * k + col];
-      out[9 * i + col] = t / L[10 * i];
+      for (int k = i + 1; k < 9; ++k) t -= L[9 * k + i] * A[9 * k + col];
+      A[9 * i + col] = t / L[10 * i];
     }
   }
+#pragma unroll 1
+  for (int k = 0; k < 81; ++k) inv[81 * (size_t)cam + k] = A[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -929,9 +965,17 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+// The panels are read exactly once per matvec and are larger than L2: stream them with an evict-first L2 policy so that
+// the camera vectors, the index arrays and the per-observation y buffer stay L2 resident.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -955,6 +999,7 @@ struct PanelStream {
   int rows_per_stage;
   int next_item;         // next item index of this warp's sequence to open
   unsigned issued;       // stages issued so far
+  uint64_t policy;       // L2 cache policy of the bulk copies
 };
 
 template <class S, int NS, int STAGE_BYTES>
@@ -975,7 +1020,7 @@ __device__ __forceinline__ bool stream_produce(PanelStream<S>& ps, const DevPtrs
   const unsigned slot = ps.issued % NS;
   if (lane == 0) {
     mbar_expect_tx(&bars[slot], bytes);
-    bulk_g2s(ring + (size_t)slot * STAGE_BYTES, ps.src, bytes, &bars[slot]);
+    bulk_g2s(ring + (size_t)slot * STAGE_BYTES, ps.src, bytes, &bars[slot], ps.policy);
   }
   ps.src += (size_t)rows * ps.row_scalars;
   ps.rows_left -= rows;
@@ -1111,7 +1156,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_matvec_small_tma(DevPtrs<S> D, c
   const int stride = gridDim.x * WARPS;
   const int first = item_begin + blockIdx.x * WARPS + wib;
   PanelStream<S> ps;
-  ps.src = nullptr; ps.rows_left = 0; ps.row_scalars = 0; ps.rows_per_stage = 1; ps.next_item = first; ps.issued = 0;
+  ps.src = nullptr; ps.rows_left = 0; ps.row_scalars = 0; ps.rows_per_stage = 1; ps.next_item = first; ps.issued = 0; ps.policy = l2_evict_first_policy();
   unsigned consumed = 0;
 #pragma unroll 1
   for (int s = 0; s < NS; ++s)
@@ -1176,91 +1221,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_matvec_large(DevPtrs<S> D, const
 //   all launched with exactly NPART blocks of 128 threads; thread per camera (9-vectors);
 //   partial sums per block in double, combined in a fixed order by the consumer kernel.
 // ------------------------------------------------------------------------------------------------
-template <class S>
-__device__ __forceinline__ void precond_apply(const S* __restrict__ inv_cam, const S* rv, S* zv) {
-#pragma unroll
-  for (int i = 0; i < 9; ++i) {
-    S a = 0;
-#pragma unroll
-    for (int jj = 0; jj < 9; ++jj) a += inv_cam[9 * i + jj] * rv[jj];
-    zv[i] = a;
-  }
-}
-
-// init: x = 0, r = b, z = M^-1 r ; partials [rz, bb, xbr=0]
-template <class S>
-__global__ void __launch_bounds__(128) k_pcg_init(DevPtrs<S> D, PcgState* st, double* part) {
-  double acc[3] = {0, 0, 0};
-  for (int cam = blockIdx.x * blockDim.x + threadIdx.x; cam < D.nc; cam += gridDim.x * blockDim.x) {
-    S rv[9], zv[9];
-#pragma unroll
-    for (int c = 0; c < 9; ++c) rv[c] = D.b[9 * (size_t)cam + c];
-    precond_apply(D.inv + 81 * (size_t)cam, rv, zv);
-    S rz = 0, bb = 0;
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      D.x[9 * (size_t)cam + c] = 0;
-      D.r[9 * (size_t)cam + c] = rv[c];
-      D.z[9 * (size_t)cam + c] = zv[c];
-      rz += rv[c] * zv[c];
-      bb += rv[c] * rv[c];
-    }
-    acc[0] += (double)rz; acc[1] += (double)bb;
-  }
-  block_sum_store<3>(acc, part);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    st->rho[0] = 1.0; st->rho[1] = 1.0; st->q0[0] = 0.0; st->q0[1] = 0.0;
-    st->iter = 0; st->done = 0; st->term = 0; st->reason = 0; st->norm_b = 0;
-  }
-}
-
-// begin iteration i: convergence test of iteration i-1, rho, beta, p update.
-// finish = 1: only evaluate the pending test (after the last iteration) and write inc = -x.
-template <class S>
-__global__ void __launch_bounds__(128) k_pcg_begin(DevPtrs<S> D, PcgState* st, const double* part, int i, double eta,
-                                                   int min_it, int finish) {
-  int done = st->done;
-  const int cur = i & 1, prev = cur ^ 1;
-  double rho = 0, beta = 0;
-  int term = 0, reason = 0;
-  double q1 = 0, zeta = 0, norm_b = 0;
-  if (!done) {
-    rho = block_sum_partials(part, NPART, 3, 0);
-    const double xbr = block_sum_partials(part, NPART, 3, 2);
-    if (i == 1) {
-      norm_b = sqrt(block_sum_partials(part, NPART, 3, 1));
-      if (norm_b == 0.0) { done = 1; term = 1; reason = 2; }
-    } else {
-      q1 = -xbr;
-      zeta = (double)(i - 1) * (q1 - st->q0[prev]) / q1;
-      if (zeta < eta && (i - 1) >= min_it) { done = 1; term = 1; reason = 1; }
-    }
-    if (!done && !finish) {
-      if (rho == 0.0 || isinf(rho)) { done = 1; term = 2; reason = 3; }
-      else if (i > 1) {
-        beta = rho / st->rho[prev];
-        if (beta == 0.0 || isinf(beta)) { done = 1; term = 2; reason = 4; }
-      }
-    }
-    if (!done && !finish) {
-      const S bs = (S)beta;
-      for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 9 * D.nc; k += gridDim.x * blockDim.x)
-        D.p[k] = (i == 1) ? D.z[k] : D.z[k] + bs * D.p[k];
-    }
-  }
-  if (finish) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 9 * D.nc; k += gridDim.x * blockDim.x) D.inc[k] = -D.x[k];
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && !st->done) {
-    if (i == 1) st->norm_b = norm_b;
-    st->rho[cur] = rho;
-    st->q0[cur] = (i == 1) ? 0.0 : q1;
-    st->last_zeta = zeta;
-    if (done) { st->done = 1; st->term = term; st->reason = reason; }
-    else if (!finish) st->iter = i;
-  }
-}
-
 // q = (sum of camera partials | y) + lambda p ; partial pq.   src9 = y vector [9nc] (already reduced)
 template <class S>
 __global__ void __launch_bounds__(128) k_pcg_q(DevPtrs<S> D, const PcgState* st, const S* __restrict__ partial,
@@ -1306,63 +1266,150 @@ __global__ void k_cam_final9(const S* __restrict__ partial, const int* __restric
   out[i] = s;
 }
 
-// mode 0: alpha = rho/pq ; x += alpha p ; r -= alpha q ; z = M^-1 r ; partials [rz, -, x.(b+r)]
-// mode 1: (refresh iteration, first half) alpha ; x += alpha p only
-// mode 2: (refresh iteration, second half) r = b - q (q = H x) ; z ; partials
+// ------------------------------------------------------------------------------------------------
+// PCG vector step on ONE thread-block cluster (hardware cluster barriers, ~0.2 us, instead of kernel boundaries):
+//   P1  q = y + lambda * v, partial v.q                       (v = p, or x in the residual-refresh half step)
+//   P2  alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z and x.(b + r)
+//   P3  Nash-Sofer test zeta = i (Q_i - Q_{i-1}) / Q_i < eta ; rho, beta ; p = z + beta p   (next iteration's p)
+// ref: cg/conjugate_gradient.hpp:161-295 ; scalars in double, vectors in Scalar, alpha/beta narrowed to Scalar.
+// mode 0 regular iteration, 1 refresh first half (stop after x += alpha p), 2 refresh second half (v = x,
+// r = b - H x), 3 initialisation (x = 0, r = b, z, rho, p = z).  part: [gridDim][4] doubles.
+// yfull != 0: y was already reduced over cameras (and shards) into D.y; else y = sum of the camera's item partials.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 template <class S>
-__global__ void __launch_bounds__(128) k_pcg_update(DevPtrs<S> D, PcgState* st, const double* part_pq, double* part,
-                                                    int i, int mode) {
+__global__ void __launch_bounds__(512) k_pcg_vec(DevPtrs<S> D, PcgState* st, const int* __restrict__ cam_item_ptr,
+                                                 double* part, S lambda, int i, int mode, int yfull, double eta, int min_it,
+                                                 int is_last) {
   if (st->done) return;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  const int n9 = 9 * D.nc;
+  const int cur = i & 1, nxt = cur ^ 1;
+  if (mode != 3) {
+    // ---- P1 ----
+    const S* vec = (mode == 2) ? D.x : D.p;
+    double acc = 0;
+    for (int e = tid; e < n9; e += nthr) {
+      S yv;
+      if (yfull) yv = D.y[e];
+      else {
+        const int cam = e / 9, c = e - 9 * cam;
+        yv = 0;
+        for (int it = cam_item_ptr[cam]; it < cam_item_ptr[cam + 1]; ++it) yv += D.partial[9 * (size_t)it + c];
+      }
+      const S pv = vec[e];
+      const S qv = yv + lambda * pv;
+      D.q[e] = qv;
+      acc += (double)(pv * qv);
+    }
+    if (mode != 2) block_sum_store4(acc, part, 0);
+    cluster_sync_all();
+  }
+  // ---- P2 ----
   double alpha = 0;
-  bool fail = false;
-  int term = 0, reason = 0;
-  double pq = 0;
-  if (mode != 2) {
-    pq = block_sum_partials(part_pq, NPART, 1, 0);
+  if (mode == 0 || mode == 1) {
+    const double pq = block_sum_partials(part, gridDim.x, 4, 0);
+    bool fail = false;
+    int term = 0, reason = 0;
     if (pq <= 0 || isinf(pq)) { fail = true; term = 0; reason = 5; }
     else {
-      alpha = st->rho[i & 1] / pq;
+      alpha = st->rho[cur] / pq;
       if (isinf(alpha)) { fail = true; term = 2; reason = 6; }
     }
-  }
-  if (fail) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) { st->done = 1; st->term = term; st->reason = reason; st->last_pq = pq; }
-    return;
+    if (fail) {  // uniform across the cluster: nobody reaches the next barrier
+      for (int e = tid; e < n9; e += nthr) D.inc[e] = -D.x[e];
+      if (tid == 0) { st->done = 1; st->term = term; st->reason = reason; st->last_pq = pq; st->iter = i; }
+      return;
+    }
+    if (tid == 0) { st->last_pq = pq; st->last_alpha = alpha; }
   }
   const S as = (S)alpha;
-  double acc[3] = {0, 0, 0};
-  for (int cam = blockIdx.x * blockDim.x + threadIdx.x; cam < D.nc; cam += gridDim.x * blockDim.x) {
-    const size_t o = 9 * (size_t)cam;
-    S xv[9], rv[9], zv[9];
-    if (mode == 1) {
-#pragma unroll
-      for (int c = 0; c < 9; ++c) D.x[o + c] = D.x[o + c] + as * D.p[o + c];
-      continue;
-    }
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      if (mode == 0) {
-        xv[c] = D.x[o + c] + as * D.p[o + c];
-        rv[c] = D.r[o + c] - as * D.q[o + c];
-        D.x[o + c] = xv[c];
-      } else {
-        xv[c] = D.x[o + c];
-        rv[c] = D.b[o + c] - D.q[o + c];
-      }
-      D.r[o + c] = rv[c];
-    }
-    precond_apply(D.inv + 81 * (size_t)cam, rv, zv);
-    S rz = 0, xbr = 0;
-#pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      D.z[o + c] = zv[c];
-      rz += rv[c] * zv[c];
-      xbr += xv[c] * (D.b[o + c] + rv[c]);
-    }
-    acc[0] += (double)rz; acc[2] += (double)xbr;
+  if (mode == 1) {
+    for (int e = tid; e < n9; e += nthr) D.x[e] = D.x[e] + as * D.p[e];
+    return;
   }
-  if (mode != 1) block_sum_store<3>(acc, part);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && mode != 2) { st->last_pq = pq; st->last_alpha = alpha; }
+  {
+    // cameras are dealt to the CTAs in contiguous ranges; inside a CTA thread (cam, a) owns element 9 cam + a, so the
+    // residual of a whole camera is produced and consumed by the same CTA (a __syncthreads() orders P2a -> P2b).
+    const int cams_per_block = (D.nc + gridDim.x - 1) / gridDim.x;
+    const int cam0 = blockIdx.x * cams_per_block;
+    const int cam1 = min(D.nc, cam0 + cams_per_block);
+    const int e0 = 9 * cam0, e1 = 9 * cam1;
+    // P2a: x and r (elementwise)
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+      S rv;
+      if (mode == 0) {
+        D.x[e] = D.x[e] + as * D.p[e];
+        rv = D.r[e] - as * D.q[e];
+      } else if (mode == 2) {
+        rv = D.b[e] - D.q[e];
+      } else {
+        D.x[e] = 0;
+        rv = D.b[e];
+      }
+      D.r[e] = rv;
+    }
+    __syncthreads();
+    // P2b: z = M^-1 r (9x9 block row per thread, ref: cg/preconditioner.hpp:122-136) and the dot products
+    double rz = 0, xbr = 0, bb = 0;
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+      const int cam = e / 9, a = e - 9 * cam;
+      const S* row = D.inv + 81 * (size_t)cam + 9 * a;
+      const S* rc = D.r + 9 * (size_t)cam;
+      S zv = 0;
+#pragma unroll
+      for (int b2 = 0; b2 < 9; ++b2) zv += row[b2] * rc[b2];
+      D.z[e] = zv;
+      const S rv = rc[a];
+      rz += (double)(rv * zv);
+      xbr += (double)(D.x[e] * (D.b[e] + rv));
+      bb += (double)(rv * rv);
+    }
+    block_sum_store4(rz, part, 1);
+    block_sum_store4(xbr, part, 2);
+    block_sum_store4(bb, part, 3);
+  }
+  cluster_sync_all();
+  // ---- P3 ----
+  const double rho_new = block_sum_partials(part, gridDim.x, 4, 1);
+  int done = 0, term = 0, reason = 0;
+  double q1 = 0, zeta = 0, beta = 0, norm_b = 0;
+  if (mode == 3) {
+    norm_b = sqrt(block_sum_partials(part, gridDim.x, 4, 3));
+    if (norm_b == 0.0) { done = 1; term = 1; reason = 2; }
+  } else {
+    const double xbr = block_sum_partials(part, gridDim.x, 4, 2);
+    q1 = -xbr;
+    zeta = (double)i * (q1 - st->q0[cur]) / q1;
+    if (zeta < eta && i >= min_it) { done = 1; term = 1; reason = 1; }
+  }
+  if (!done) {
+    if (rho_new == 0.0 || isinf(rho_new)) { done = 1; term = 2; reason = 3; }
+    else if (mode != 3) {
+      beta = rho_new / st->rho[cur];
+      if (beta == 0.0 || isinf(beta)) { done = 1; term = 2; reason = 4; }
+    }
+  }
+  if (!done && !is_last) {
+    const S bs = (S)beta;
+    for (int e = tid; e < n9; e += nthr) D.p[e] = (mode == 3) ? D.z[e] : D.z[e] + bs * D.p[e];
+  }
+  if (done || is_last) {
+    for (int e = tid; e < n9; e += nthr) D.inc[e] = -D.x[e];
+  }
+  if (tid == 0) {
+    st->rho[nxt] = rho_new;  // iteration i+1 reads slot (i+1)&1
+    st->q0[nxt] = (mode == 3) ? 0.0 : q1;
+    st->last_zeta = zeta;
+    st->iter = i;
+    if (mode == 3) { st->norm_b = norm_b; st->term = 0; st->reason = 0; }
+    if (done) { st->done = 1; st->term = term; st->reason = reason; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -87,6 +87,8 @@ struct Solver : rba_handle {
   ReduceItem* d_pb_items = nullptr; int* d_pb_item_ptr = nullptr; int n_pb_items = 0;
   double* d_part = nullptr;      // [NPART][3]
   double* d_part_pq = nullptr;   // [NPART]
+  double* d_part4 = nullptr;     // [grid][4] partials of the fused PCG step
+  int pcg_cluster = 16;
   double* d_epart = nullptr;     // [EBLOCKS][6]
   double* d_red = nullptr;       // [8] reduced doubles (error / l_diff)
   int* d_flags = nullptr;        // [4] bad flags
@@ -228,7 +230,7 @@ struct Solver : rba_handle {
     TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
     TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
     TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
-    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART));
+    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4));
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_state, 1));
 #undef TRY
@@ -248,6 +250,23 @@ struct Solver : rba_handle {
     if (k4_smem_small > 200 * 1024) { g_err = "matvec scratch exceeds shared memory"; return RBA_ERR_UNSUPPORTED; }
     CU(cudaFuncSetAttribute(k_matvec_small<S, K4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k4_smem_small, 1024)));
     CU(cudaFuncSetAttribute((k_matvec_large<S, K4_WARPS, KPMAX>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k4_smem_small, 1024)));
+    {
+      // the PCG vector step runs on one thread-block cluster (16 CTAs if the device grants it, else 8)
+      CU(cudaFuncSetAttribute(k_pcg_vec<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      pcg_cluster = 16;
+      if (const char* e = getenv("RBA_PCG_CLUSTER")) pcg_cluster = std::max(1, std::min(atoi(e), 16));
+      for (; pcg_cluster > 1; pcg_cluster >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pcg_cluster); cfg.blockDim = dim3(512);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = pcg_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_pcg_vec<S>, &cfg) == cudaSuccess && ncl >= 1) break;
+        cudaGetLastError();
+      }
+    }
     {
       const char* e = getenv("RBA_MATVEC");
       use_tma = !(e && std::string(e) == "ldg");
@@ -398,6 +417,11 @@ struct Solver : rba_handle {
 
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
   void matvec_launch(const S* xvec, const int* done) {
+    matvec_kernels(xvec, done);
+    k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, done);
+    ++launches;
+  }
+  void matvec_kernels(const S* xvec, const int* done) {
     const int nitems = (int)L.items.size();
     if (L.n_items_large > 0) {
       k_matvec_large<S, K4_WARPS, KPMAX><<<grid_for(L.n_items_large, K4_WARPS, 4), K4_WARPS * 32, k4_smem_small, stream>>>(
@@ -413,9 +437,29 @@ struct Solver : rba_handle {
             D, d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done);
       ++launches;
     }
-    k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, done);
-    ++launches;
     ++tm.matvec_launches;
+  }
+  int pcg_vec(int i, int mode, int yfull, int is_last, S lambda) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pcg_cluster); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pcg_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k_pcg_vec<S>, D, d_state, (const int*)d_csr_y_item_ptr, d_part4, lambda, i, mode, yfull,
+                          (double)opt.eta, (int)opt.min_linear_solver_iterations, is_last));
+    ++launches;
+    return RBA_OK;
+  }
+  // finish one operator application inside PCG (H v for v = p in mode 0/1, x in mode 2) and do the vector step
+  int pcg_apply(int i, int mode, int is_last, S lambda) {
+    k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, &d_state->done);
+    ++launches;
+    if (opt.nranks == 1) return pcg_vec(i, mode, 0, is_last, lambda);
+    k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, d_csr_y_item_ptr, nc, D.y, &d_state->done);
+    ++launches;
+    int rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
+    return pcg_vec(i, mode, 1, is_last, lambda);
   }
   // q_out = H vec = sum + lambda vec ; optional partial p.q
   int matvec_finish(const S* vec, S* out, S lambda, PcgState* st, double* part) {
@@ -454,11 +498,11 @@ struct Solver : rba_handle {
     damping_valid = true;
     // PCG (ref: cg/conjugate_gradient.hpp:113-298 ; linearizor_base.cpp:81-103)
     rc = start(ev_pcg); if (rc) return rc;
-    k_pcg_init<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part);
-    ++launches;
+    CU(cudaMemsetAsync(d_state, 0, sizeof(PcgState), stream));
     const int max_it = std::max(opt.max_linear_solver_iterations, 1);
     const int period = opt.residual_reset_period;
     const int chk = opt.pcg_check_period;
+    rc = pcg_vec(0, 3, 0, 0, lambda); if (rc) return rc;  // x = 0, r = b, z = M^-1 r, rho, p = z
     int i = 1;
     int pending[2] = {0, 0};
     int slot = 0;
@@ -466,20 +510,14 @@ struct Solver : rba_handle {
     while (i <= max_it && !finished) {
       const int chunk_end = std::min(i + chk - 1, max_it);
       for (; i <= chunk_end; ++i) {
-        k_pcg_begin<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part, i, opt.eta, opt.min_linear_solver_iterations, 0);
-        ++launches;
-        matvec_launch(D.p, &d_state->done);
-        rc = matvec_finish(D.p, D.q, lambda, d_state, d_part_pq); if (rc) return rc;
+        const int is_last = (i == max_it) ? 1 : 0;
+        matvec_kernels(D.p, &d_state->done);
         if (i % period == 0) {
-          k_pcg_update<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part_pq, d_part, i, 1);
-          ++launches;
-          matvec_launch(D.x, &d_state->done);
-          rc = matvec_finish(D.x, D.q, lambda, d_state, nullptr); if (rc) return rc;
-          k_pcg_update<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part_pq, d_part, i, 2);
-          ++launches;
+          rc = pcg_apply(i, 1, 0, lambda); if (rc) return rc;
+          matvec_kernels(D.x, &d_state->done);
+          rc = pcg_apply(i, 2, is_last, lambda); if (rc) return rc;
         } else {
-          k_pcg_update<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part_pq, d_part, i, 0);
-          ++launches;
+          rc = pcg_apply(i, 0, is_last, lambda); if (rc) return rc;
         }
       }
       CU(cudaMemcpyAsync(&h_state[slot], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
@@ -493,8 +531,6 @@ struct Solver : rba_handle {
       }
       slot = other;
     }
-    k_pcg_begin<S><<<NPART, 128, 0, stream>>>(D, d_state, d_part, i, opt.eta, opt.min_linear_solver_iterations, 1);
-    ++launches;
     CU(cudaMemcpyAsync(&h_state[0], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
     if (inc_out) CU(cudaMemcpyAsync(inc_out, D.inc, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
     rc = stop(ev_pcg); if (rc) return rc;

@@ -19,7 +19,8 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 seen = set()
 for row in r[2:]:
     name = re.sub(r'\(.*', '', row[hdr.index('Kernel Name')])
-    if len(sys.argv) > 2 and sys.argv[2] not in name: continue
+    flt = [a for a in sys.argv[2:] if not a.startswith('--')]
+    if flt and flt[0] not in name: continue
     if name in seen and '--all' not in sys.argv: continue
     seen.add(name)
     print('--- kernel', name[:70])
