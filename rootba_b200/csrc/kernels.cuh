@@ -67,8 +67,9 @@ struct DevPtrs {
   const int* slot_cam; const int* slot_lm; const S* slot_xy; int nslots;
   // linearization storage
   S* panel;      // Q2^T Jp panels, tile layout
-  S* rec;        // [nslots][48] = [jp(2x9) scaled | q1d(3x9) | pad 3]
-  S* q1u;        // [nslots][27] undamped Q1^T Jp
+  S* jp;         // [nslots][20] scaled, weighted pose Jacobian rows (2x9) + 2 pad   (16-byte aligned records)
+  S* q1u;        // [nslots][28] undamped Q1^T Jp (3x9) + 1 pad
+  S* q1d;        // [nslots][28] damped   Q1^T Jp (3x9) + 1 pad
   S* jl;         // [nslots][6]  scaled Jl (2x3)
   S* res;        // [nslots][2]  weighted residual
   S* lmk;        // [nsorted][24] Ru(6) q1r_u(3) Rd(6) q1r_d(3) Jl_col_scale(3) pad
@@ -380,6 +381,49 @@ __global__ void k_scaling(const S* diag2, S* scaling, int n, S eps) {
   if (i < n) scaling[i] = S(1) / (eps + sqrt(diag2[i]));
 }
 
+
+// ---- warp-cooperative copies between a tile's contiguous global region and scratch (16-byte vectors) ----
+template <class S>
+__device__ __forceinline__ void warp_copy_in(S* __restrict__ dst, const S* __restrict__ src, int count, int lane) {
+  using V4 = typename ST<S>::V4;
+  constexpr int VW = 16 / sizeof(S) >= 4 ? 4 : 2;  // scalars per 16-byte (f32) / 32-byte (f64 double4 is 32 B: use 2)
+  if (sizeof(S) == 4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int e = lane; e < count / 4; e += 32) d4[e] = __ldg(s4 + e);
+  } else {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int e = lane; e < count / 2; e += 32) d2[e] = __ldg(s2 + e);
+  }
+  (void)VW;
+}
+template <class S>
+__device__ __forceinline__ void warp_copy_out(S* __restrict__ dst, const S* __restrict__ src, int count, int lane) {
+  if (sizeof(S) == 4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int e = lane; e < count / 4; e += 32) d4[e] = s4[e];
+  } else {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int e = lane; e < count / 2; e += 32) d2[e] = s2[e];
+  }
+}
+// scratch of a tile kernel: shared memory when the tile fits, else a per-warp slice of a global buffer
+template <class S>
+struct Scratch {
+  S* gbase;          // global scratch (may be null when every tile fits in shared memory)
+  long long gstride; // scalars per warp
+  int smem_cap;      // scalars of shared memory per warp
+};
+template <class S>
+__device__ __forceinline__ S* scratch_ptr(const Scratch<S>& sc, S* smem_warp, int need) {
+  if (need <= sc.smem_cap) return smem_warp;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  return sc.gbase + w * sc.gstride;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1b  linearize + Jl scaling + Householder QR of the 3 landmark columns + write marginalised panel
 //   ref: ipp:88-147 (linearize_landmark), :571-587 (scale_Jl_cols), :717-743 (perform_qr_householder),
@@ -391,19 +435,23 @@ __global__ void k_scaling(const S* diag2, S* scaling, int n, S eps) {
 //   the coalesced panel layout.
 // ------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, int scratch_per_warp, int* bad_flag) {
+__global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scratch<S> sc, int* bad_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using V2 = typename ST<S>::V2;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  S* ws = reinterpret_cast<S*>(smem_raw) + (size_t)wib * scratch_per_warp;
+  S* ws_smem = reinterpret_cast<S*>(smem_raw) + (size_t)wib * sc.smem_cap;
   const S eps = (S)o.jacobi_eps;
   for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
     const TileInfo T = D.tiles[t];
     const int n = T.n, G = T.G, KP = T.KP;
     const int g = lane / G, j = lane - g * G;
     const bool active = g < T.nvalid;
-    S* sJ = ws + (size_t)g * 32 * n;  // [n][26]: jp row0 (9) | jp row1 (9) | jl row0 (3) | jl row1 (3) | r (2)
+    const int Wn = (32 / G) * n;
+    S* ws = scratch_ptr(sc, ws_smem, Wn * 60 + 64);
+    const int GS = 32 * n + 1;        // per-landmark scratch stride, odd => group-broadcast reads hit distinct banks
+    S* sJ = ws + (size_t)g * GS;      // [n][26]: jp row0 (9) | jp row1 (9) | jl row0 (3) | jl row1 (3) | r (2)
     S* sV = sJ + 26 * n;              // [2n][3] Householder vectors
+    S* sQ = ws + (((size_t)(32 / G) * GS + 3) & ~(size_t)3);  // [W*n][28] staging of the undamped Q1^T Jp rows
     const int slot0 = T.slot_base + g * n;
     const int sidx = T.lm_base + g;
     S pw[3] = {0, 0, 0};
@@ -474,20 +522,24 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, int
       for (int c = 0; c < 3; ++c) { e[c] *= jls[c]; e[3 + c] *= jls[c]; }
     }
     __syncwarp();
-    // ---- write the per-observation records (scaled Jp, scaled Jl, weighted residual) ----
-    if (active) {
-      for (int i = j; i < n; i += G) {
-        const S* e = sJ + 26 * i;
-        S* rc = D.rec + 48 * (size_t)(slot0 + i);
-#pragma unroll
-        for (int c = 0; c < 18; ++c) rc[c] = e[c];
-        S* jo = D.jl + 6 * (size_t)(slot0 + i);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) jo[c] = e[18 + c];
-        D.res[2 * (size_t)(slot0 + i)] = e[24];
-        D.res[2 * (size_t)(slot0 + i) + 1] = e[25];
+    // ---- write the per-observation records (scaled Jp, scaled Jl, weighted residual), coalesced per landmark ----
+    for (int g2 = 0; g2 < T.nvalid; ++g2) {
+      const S* src = ws + (size_t)g2 * GS;
+      const size_t sb = (size_t)(T.slot_base + g2 * n);
+      S* jo = D.jp + 20 * sb;
+      for (int e = lane; e < n * 20; e += 32) {
+        const int i2 = e / 20, k = e - 20 * i2;
+        jo[e] = k < 18 ? src[26 * i2 + k] : S(0);
       }
+      S* lo = D.jl + 6 * sb;
+      for (int e = lane; e < n * 6; e += 32) {
+        const int i2 = e / 6, k = e - 6 * i2;
+        lo[e] = src[26 * i2 + 18 + k];
+      }
+      S* ro = D.res + 2 * sb;
+      for (int e = lane; e < n * 2; e += 32) ro[e] = src[26 * (e >> 1) + 24 + (e & 1)];
     }
+    __syncwarp();
     // ---- c. Householder QR of A = [Jl | r] (2n x 4), rows rho = 2i + parity ----
 #define A_AT(rho, c) sJ[26 * ((rho) >> 1) + ((c) < 3 ? 18 + 3 * ((rho)&1) + (c) : 24 + ((rho)&1))]
     S tau[3];
@@ -584,25 +636,47 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, int
         w1[v] = tau[1] * (z1 - g10 * w0[v]);
         w2[v] = tau[2] * (z2 - g20 * w0[v] - g21 * w1[v]);
       }
-      for (int r = 0; r < nrows; ++r) {
+      // rows 0..2 = Q1^T Jp (undamped) -> staging
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
         const S v0 = sV[3 * r], v1 = sV[3 * r + 1], v2 = sV[3 * r + 2];
-        S out[2];
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const S sel = (r == r2i[v]) ? a0[v] : ((r == r2i[v] + 1) ? a1[v] : S(0));
-          out[v] = sel - (w0[v] * v0 + w1[v] * v1 + w2[v] * v2);
+          if (vc[v]) sQ[28 * (g * n + oi[v]) + 9 * r + op[v]] = sel - (w0[v] * v0 + w1[v] * v1 + w2[v] * v2);
         }
-        if (r < 3) {
-          if (active) {
+      }
+      // rows 3..2n-1 = Q2^T Jp: out = -V[r] . w ; the two rows that carry the original Jacobian entries are patched below
+      if (active) {
+        V2* pk = ptile + (size_t)k * 32 + lane;
+        const S nw00 = vc[0] ? -w0[0] : S(0), nw01 = vc[0] ? -w1[0] : S(0), nw02 = vc[0] ? -w2[0] : S(0);
+        const S nw10 = vc[1] ? -w0[1] : S(0), nw11 = vc[1] ? -w1[1] : S(0), nw12 = vc[1] ? -w2[1] : S(0);
+        const S* vp = sV + 9;
+#pragma unroll 4
+        for (int r = 3; r < nrows; ++r, vp += 3) {
+          const S v0 = vp[0], v1 = vp[1], v2 = vp[2];
+          pk[(size_t)(r - 3) * KP * 32] = mk2(nw00 * v0 + nw01 * v1 + nw02 * v2, nw10 * v0 + nw11 * v1 + nw12 * v2);
+        }
+        // patch: rows 2i and 2i+1 of each column also carry a0 / a1 (same lane re-writes its own element)
 #pragma unroll
-            for (int v = 0; v < 2; ++v)
-              if (vc[v]) D.q1u[27 * (size_t)(slot0 + oi[v]) + 9 * r + op[v]] = out[v];
+        for (int v = 0; v < 2; ++v) {
+          if (!vc[v]) continue;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int r = r2i[v] + q;
+            if (r >= 3) {
+              const S* vq = sV + 3 * r;
+              const S val = (q == 0 ? a0[v] : a1[v]) - (w0[v] * vq[0] + w1[v] * vq[1] + w2[v] * vq[2]);
+              S* dst = reinterpret_cast<S*>(pk + (size_t)(r - 3) * KP * 32) + v;
+              *dst = val;
+            }
           }
-        } else if (active) {
-          ptile[((size_t)(r - 3) * KP + k) * 32 + lane] = mk2(vc[0] ? out[0] : S(0), vc[1] ? out[1] : S(0));
         }
       }
     }
+    for (int e = lane; e < Wn; e += 32) sQ[28 * e + 27] = 0;  // pad
+    __syncwarp();
+    warp_copy_out(D.q1u + 28 * (size_t)T.slot_base, sQ, T.nvalid * n * 28, lane);
     __syncwarp();
   }
 }
@@ -639,84 +713,122 @@ __device__ __forceinline__ void rot_apply(const Rot<S>& g, S& x, S& y) {
   y = -g.s * xi + g.c * yi;
 }
 
+// scratch scalars per warp for a tile (host mirrors this in Solver::init)
+__host__ __device__ inline int stage2_need(int n, int G, int KP) {
+  const int W = 32 / G, Wn = W * n;
+  const int CS = (2 * G * KP) | 1;
+  return Wn * (28 + 20 + 2 + 9) + (G < 32 ? 3 * W * CS : 0) + W * 16;
+}
+
 template <class S>
-__global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda) {
+__global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<S> sc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   using V2 = typename ST<S>::V2;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  S* ws_smem = reinterpret_cast<S*>(smem_raw) + (size_t)wib * sc.smem_cap;
   for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
     const TileInfo T = D.tiles[t];
-    const int n = T.n, G = T.G, KP = T.KP;
-    const int g = lane / G, j = lane - g * G;
-    const bool active = g < T.nvalid;
-    const int slot0 = T.slot_base + g * n;
-    const int sidx = T.lm_base + g;
-    // rotations from R (3x3 upper) and sqrt(lambda) (ref: ipp:188-209)
-    Rot<S> rot[6];
-    S Rw[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Dw[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    S rr[3] = {0, 0, 0}, dr[3] = {0, 0, 0};
-    if (active) {
-      const S* lk = D.lmk + 24 * (size_t)sidx;
-      Rw[0][0] = lk[0]; Rw[0][1] = lk[1]; Rw[0][2] = lk[2]; Rw[1][1] = lk[3]; Rw[1][2] = lk[4]; Rw[2][2] = lk[5];
-      rr[0] = lk[6]; rr[1] = lk[7]; rr[2] = lk[8];
-    }
-    if (lambda == S(0)) {
+    const int n = T.n, G = T.G, KP = T.KP, W = 32 / G, Wn = W * n;
+    const int ncols = 9 * n;
+    const int CS = (2 * G * KP) | 1;
+    S* ws = scratch_ptr(sc, ws_smem, stage2_need(n, G, KP));
+    S* sQ = ws;                 // [Wn][28]  q1u in, q1d out (in place)
+    S* sJ = sQ + Wn * 28;       // [Wn][20]  scaled pose Jacobian rows
+    S* sR = sJ + Wn * 20;       // [Wn][2]   weighted residual
+    S* sG = sR + Wn * 2;        // [Wn][9]   gradient contribution per observation
+    S* sRot = sG + Wn * 9;      // [W][16]   6 rotations (c,s) + damped Q1^T r (3)
+    S* sD = sRot + W * 16;      // [3][W][CS] damping rows in (landmark, column) order (G < 32 only)
+    const int nsl = T.nvalid * n;
+    // ---- coalesced loads of the tile's records ----
+    warp_copy_in(sQ, D.q1u + 28 * (size_t)T.slot_base, nsl * 28, lane);
+    warp_copy_in(sJ, D.jp + 20 * (size_t)T.slot_base, nsl * 20, lane);
+    for (int e = lane; e < nsl * 2; e += 32) sR[e] = D.res[2 * (size_t)T.slot_base + e];
+    // ---- rotations of landmark `lane` (ref: ipp:188-209), Eigen makeGivens / applyOnTheLeft ----
+    if (lane < T.nvalid) {
+      S* lk = D.lmk + 24 * (size_t)(T.lm_base + lane);
+      S Rw[3][3] = {{lk[0], lk[1], lk[2]}, {0, lk[3], lk[4]}, {0, 0, lk[5]}};
+      S Dw[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      S rr[3] = {lk[6], lk[7], lk[8]}, dr[3] = {0, 0, 0};
+      S* ro = sRot + 16 * lane;
+      if (lambda == S(0)) {
 #pragma unroll
-      for (int q = 0; q < 6; ++q) { rot[q].c = 1; rot[q].s = 0; }
-    } else {
-      const S sl = sqrt(lambda);
-      Dw[0][0] = sl; Dw[1][1] = sl; Dw[2][2] = sl;
-      int q = 0;
+        for (int q = 0; q < 6; ++q) { ro[2 * q] = 1; ro[2 * q + 1] = 0; }
+      } else {
+        const S sl = sqrt(lambda);
+        Dw[0][0] = sl; Dw[1][1] = sl; Dw[2][2] = sl;
+        int q = 0;
 #pragma unroll
-      for (int nn = 0; nn < 3; ++nn)
+        for (int nn = 0; nn < 3; ++nn)
 #pragma unroll
-        for (int m = 0; m <= nn; ++m) {
-          const int d = nn - m;
-          const Rot<S> gq = make_givens(Rw[nn][nn], Dw[d][nn]);
-          rot[q++] = gq;
+          for (int m = 0; m <= nn; ++m) {
+            const int d = nn - m;
+            const Rot<S> gq = make_givens(Rw[nn][nn], Dw[d][nn]);
+            ro[2 * q] = gq.c; ro[2 * q + 1] = gq.s;
+            ++q;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) rot_apply(gq, Dw[d][c], Rw[nn][c]);
-          rot_apply(gq, dr[d], rr[nn]);
-        }
-    }
-    if (active && j == 0) {
-      S* lk = D.lmk + 24 * (size_t)sidx;
+            for (int c = 0; c < 3; ++c) rot_apply(gq, Dw[d][c], Rw[nn][c]);
+            rot_apply(gq, dr[d], rr[nn]);
+          }
+      }
+      ro[12] = rr[0]; ro[13] = rr[1]; ro[14] = rr[2];
       lk[9] = Rw[0][0]; lk[10] = Rw[0][1]; lk[11] = Rw[0][2]; lk[12] = Rw[1][1]; lk[13] = Rw[1][2]; lk[14] = Rw[2][2];
       lk[15] = rr[0]; lk[16] = rr[1]; lk[17] = rr[2];
     }
+    __syncwarp();
+    // ---- per column (observation-major order): q1d, damping rows, gradient ----
     V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off);
-    const int ncols = 9 * n;
-    for (int k = 0; k < KP; ++k) {
-      const int c0 = 2 * j + 2 * G * k;
-      S drow[3][2];
+    S* prow = D.panel + T.panel_off + (size_t)(2 * n - 3) * KP * 64;  // first damping row
+    {
+      int g2 = 0, c = lane;
+      while (c >= ncols) { c -= ncols; ++g2; }
+      while (g2 < T.nvalid) {
+        const int i = c / 9, p = c - 9 * i;
+        const int sl = g2 * n + i;
+        const S* ro = sRot + 16 * g2;
+        S* q = sQ + 28 * sl + p;
+        S qv[3] = {q[0], q[9], q[18]}, dv[3] = {0, 0, 0};
+        int qi = 0;
 #pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const int c = c0 + v;
-        const bool vc = active && c < ncols;
-        S qv[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
-        if (vc) {
-          const int i = c / 9, p = c - 9 * i;
-          const size_t s = (size_t)(slot0 + i);
-          const S* qu = D.q1u + 27 * s + p;
-          qv[0] = qu[0]; qv[1] = qu[9]; qv[2] = qu[18];
-          int q = 0;
+        for (int nn = 0; nn < 3; ++nn)
 #pragma unroll
-          for (int nn = 0; nn < 3; ++nn)
+          for (int m = 0; m <= nn; ++m) {
+            Rot<S> gq; gq.c = ro[2 * qi]; gq.s = ro[2 * qi + 1]; ++qi;
+            rot_apply(gq, dv[nn - m], qv[nn]);
+          }
+        q[0] = qv[0]; q[9] = qv[1]; q[18] = qv[2];
+        // gradient of the reduced system: b_c = jp_c^T r_i - q1d_c^T (Q1^T r)_d
+        sG[9 * sl + p] = sJ[20 * sl + p] * sR[2 * sl] + sJ[20 * sl + 9 + p] * sR[2 * sl + 1] -
+                         (qv[0] * ro[12] + qv[1] * ro[13] + qv[2] * ro[14]);
+        if (G == 32) {
+          // W = 1: the panel row layout [k][lane][2] is the natural column order
 #pragma unroll
-            for (int m = 0; m <= nn; ++m) rot_apply(rot[q++], dv[nn - m], qv[nn]);
-          S* rc = D.rec + 48 * s;
-          rc[18 + p] = qv[0]; rc[27 + p] = qv[1]; rc[36 + p] = qv[2];
-          // gradient of the reduced system: b_c = jp_c^T r_i - q1d_c^T (Q1^T r)_d
-          const S gc = rc[p] * D.res[2 * s] + rc[9 + p] * D.res[2 * s + 1] - (qv[0] * rr[0] + qv[1] * rr[1] + qv[2] * rr[2]);
-          D.yobs[9 * s + p] = gc;
+          for (int d = 0; d < 3; ++d) prow[(size_t)d * KP * 64 + c] = dv[d];
+        } else {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) sD[(d * W + g2) * CS + c] = dv[d];
         }
-        drow[0][v] = dv[0]; drow[1][v] = dv[1]; drow[2][v] = dv[2];
-      }
-      if (active) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-          ptile[((size_t)(2 * n - 3 + d) * KP + k) * 32 + lane] = mk2(drow[d][0], drow[d][1]);
+        c += 32;
+        while (c >= ncols) { c -= ncols; ++g2; }
       }
     }
+    __syncwarp();
+    // ---- coalesced stores ----
+    warp_copy_out(D.q1d + 28 * (size_t)T.slot_base, sQ, nsl * 28, lane);
+    for (int e = lane; e < nsl * 9; e += 32) D.yobs[9 * (size_t)T.slot_base + e] = sG[e];
+    if (G < 32) {
+      const int g = lane / G, j = lane - g * G;
+      if (g < T.nvalid) {
+        for (int k = 0; k < KP; ++k) {
+          const int c = 2 * j + 2 * G * k;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const S* row = sD + (d * W + g) * CS;
+            ptile[((size_t)(2 * n - 3 + d) * KP + k) * 32 + lane] = mk2(c < ncols ? row[c] : S(0), c + 1 < ncols ? row[c + 1] : S(0));
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -727,10 +839,9 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda) {
 //   be finer; we use thread per item-of-32 built on the host (pb_items).
 // ------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(128) k_precond_partial(const S* __restrict__ rec, const int* __restrict__ slots,
-                                                          const ReduceItem* __restrict__ items, int nitems,
-                                                          int schur, S* __restrict__ pblk) {
-  using V4 = typename ST<S>::V4;
+__global__ void __launch_bounds__(128) k_precond_partial(const S* __restrict__ jp, const S* __restrict__ q1d,
+                                                          const int* __restrict__ slots, const ReduceItem* __restrict__ items,
+                                                          int nitems, int schur, S* __restrict__ pblk) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= nitems) return;
   const ReduceItem I = items[it];
@@ -738,21 +849,32 @@ __global__ void __launch_bounds__(128) k_precond_partial(const S* __restrict__ r
 #pragma unroll
   for (int k = 0; k < 45; ++k) acc[k] = 0;
   for (int e = I.begin; e < I.end; ++e) {
-    const V4* rp = reinterpret_cast<const V4*>(rec + 48 * (size_t)slots[e]);
+    const size_t sl = (size_t)slots[e];
     S v[48];
+    if (sizeof(S) == 4) {
+      const float4* a4 = reinterpret_cast<const float4*>(jp + 20 * sl);
+      const float4* b4 = reinterpret_cast<const float4*>(q1d + 28 * sl);
 #pragma unroll
-    for (int q = 0; q < 12; ++q) {
-      const V4 t = rp[q];
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      for (int q = 0; q < 5; ++q) { const float4 t = __ldg(a4 + q); v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+#pragma unroll
+      for (int q = 0; q < 7; ++q) { const float4 t = __ldg(b4 + q); v[20 + 4 * q] = t.x; v[21 + 4 * q] = t.y; v[22 + 4 * q] = t.z; v[23 + 4 * q] = t.w; }
+    } else {
+      const double2* a2 = reinterpret_cast<const double2*>(jp + 20 * sl);
+      const double2* b2 = reinterpret_cast<const double2*>(q1d + 28 * sl);
+#pragma unroll
+      for (int q = 0; q < 10; ++q) { const double2 t = __ldg(a2 + q); v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+#pragma unroll
+      for (int q = 0; q < 14; ++q) { const double2 t = __ldg(b2 + q); v[20 + 2 * q] = t.x; v[21 + 2 * q] = t.y; }
     }
+    // v[0..17] = jp rows, v[20..46] = q1d rows
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 9; ++a)
 #pragma unroll
       for (int b = a; b < 9; ++b) {
-        S s = v[a] * v[b] + v[9 + a] * v[9 + b];
-        if (schur) s -= v[18 + a] * v[18 + b] + v[27 + a] * v[27 + b] + v[36 + a] * v[36 + b];
-        acc[k++] += s;
+        S sacc = v[a] * v[b] + v[9 + a] * v[9 + b];
+        if (schur) sacc -= v[20 + a] * v[20 + b] + v[29 + a] * v[29 + b] + v[38 + a] * v[38 + b];
+        acc[k++] += sacc;
       }
   }
   S* o = pblk + 48 * (size_t)it;
@@ -783,43 +905,63 @@ __global__ void __launch_bounds__(64) k_precond_invert(const S* __restrict__ src
                                                         S* __restrict__ blocks_out, S* __restrict__ inv) {
   const int cam = blockIdx.x * blockDim.x + threadIdx.x;
   if (cam >= nc) return;
-  S A[81], L[81];
-#pragma unroll 1
-  for (int k = 0; k < 81; ++k) { A[k] = src[81 * (size_t)cam + k]; L[k] = 0; }
-#pragma unroll 1
-  for (int d = 0; d < 9; ++d) A[10 * d] += lambda;
+  // everything is fully unrolled so that the 9x9 block lives in registers (no local-memory round trips)
+  S A[9][9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r)
+#pragma unroll
+    for (int c = 0; c < 9; ++c) A[r][c] = src[81 * (size_t)cam + 9 * r + c];
+#pragma unroll
+  for (int d = 0; d < 9; ++d) A[d][d] += lambda;
   if (blocks_out)
-#pragma unroll 1
-    for (int k = 0; k < 81; ++k) blocks_out[81 * (size_t)cam + k] = A[k];
-#pragma unroll 1
+#pragma unroll
+    for (int r = 0; r < 9; ++r)
+#pragma unroll
+      for (int c = 0; c < 9; ++c) blocks_out[81 * (size_t)cam + 9 * r + c] = A[r][c];
+  // in-place Cholesky of the upper-stored symmetric block: lower factor L in A[i][j], i >= j
+  // (selfadjointView<Upper>().llt(), ref: cg/preconditioner.hpp:107-113)
+#pragma unroll
   for (int jj = 0; jj < 9; ++jj) {
-    S s = A[10 * jj];
-    for (int k = 0; k < jj; ++k) s -= L[9 * jj + k] * L[9 * jj + k];
-    const S d = sqrt(s);
-    L[10 * jj] = d;
+    S sdiag = A[jj][jj];
+#pragma unroll
+    for (int k = 0; k < jj; ++k) sdiag -= A[jj][k] * A[jj][k];
+    const S d = sqrt(sdiag);
+    A[jj][jj] = d;
+#pragma unroll
     for (int i = jj + 1; i < 9; ++i) {
-      S t = A[9 * jj + i];
-      for (int k = 0; k < jj; ++k) t -= L[9 * i + k] * L[9 * jj + k];
-      L[9 * i + jj] = t / d;
+      S t = A[jj][i];  // upper entry (jj, i) of the symmetric input
+#pragma unroll
+      for (int k = 0; k < jj; ++k) t -= A[i][k] * A[jj][k];
+      A[i][jj] = t / d;
     }
   }
-  // A is no longer needed: reuse it for the inverse
-#pragma unroll 1
-  for (int col = 0; col < 9; ++col) {
-    S yv[9];
-    for (int i = 0; i < 9; ++i) {
-      S t = (i == col) ? S(1) : S(0);
-      for (int k = 0; k < i; ++k) t -= L[9 * i + k] * yv[k];
-      yv[i] = t / L[10 * i];
-    }
-    for (int i = 8; i >= 0; --i) {
-      S t = yv[i];
-      for (int k = i + 1; k < 9; ++k) t -= L[9 * k + i] * A[9 * k + col];
-      A[9 * i + col] = t / L[10 * i];
+  // Li = L^-1 (lower triangular), stored in the strict upper part + a separate diagonal
+  S Li[9][9];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) {
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      if (r < c) Li[r][c] = 0;
+      else {
+        S t = (r == c) ? S(1) : S(0);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) if (k >= c && k < r) t -= A[r][k] * Li[k][c];
+        Li[r][c] = t / A[r][r];
+      }
     }
   }
-#pragma unroll 1
-  for (int k = 0; k < 81; ++k) inv[81 * (size_t)cam + k] = A[k];
+  // inverse = Li^T Li
+  S* out = inv + 81 * (size_t)cam;
+#pragma unroll
+  for (int r = 0; r < 9; ++r)
+#pragma unroll
+    for (int c = r; c < 9; ++c) {
+      S t = 0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) if (k >= c) t += Li[k][r] * Li[k][c];
+      out[9 * r + c] = t;
+      out[9 * c + r] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1417,28 +1559,60 @@ __global__ void __launch_bounds__(512) k_pcg_vec(DevPtrs<S> D, PcgState* st, con
 //     Q^T (Jp dp + Jl inc) has the same norm / inner product with Q^T r as (Jp dp + Jl inc) with r.
 // ------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* __restrict__ pose_inc,
+__global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* __restrict__ pose_inc, Scratch<S> sc,
                                                           double* partials, int* bad_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  S* ws_smem = reinterpret_cast<S*>(smem_raw) + (size_t)wib * sc.smem_cap;
   double ld[1] = {0};
   for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
     const TileInfo T = D.tiles[t];
-    const int n = T.n, G = T.G;
+    const int n = T.n, G = T.G, W = 32 / G, Wn = W * n;
     const int g = lane / G, j = lane - g * G;
     const bool active = g < T.nvalid;
-    const int slot0 = T.slot_base + g * n;
     const int sidx = T.lm_base + g;
-    // s_m = sum_c q1d[m][c] dp[c]
+    const int nsl = T.nvalid * n;
+    S* ws = scratch_ptr(sc, ws_smem, Wn * 68);
+    S* sQ = ws;              // [Wn][28] damped Q1^T Jp
+    S* sJ = sQ + Wn * 28;    // [Wn][20] scaled pose Jacobian rows
+    S* sL = sJ + Wn * 20;    // [Wn][6]  scaled landmark Jacobian rows
+    S* sR = sL + Wn * 6;     // [Wn][2]  weighted residual
+    S* sP = sR + Wn * 2;     // [Wn][9]  gathered pose increment (+3 spare)
+    warp_copy_in(sQ, D.q1d + 28 * (size_t)T.slot_base, nsl * 28, lane);
+    warp_copy_in(sJ, D.jp + 20 * (size_t)T.slot_base, nsl * 20, lane);
+    for (int e = lane; e < nsl * 6; e += 32) sL[e] = D.jl[6 * (size_t)T.slot_base + e];
+    for (int e = lane; e < nsl * 2; e += 32) sR[e] = D.res[2 * (size_t)T.slot_base + e];
+    {  // gather of the pose increments: index loads first, then the dependent loads (two round trips per 18*32 entries)
+      for (int base = 0; base < nsl * 9; base += 18 * 32) {
+        int off[18];
+#pragma unroll
+        for (int t = 0; t < 18; ++t) {
+          const int e = base + lane + 32 * t;
+          const int sl = e / 9, c = e - 9 * sl;
+          off[t] = e < nsl * 9 ? 9 * __ldg(D.slot_cam + T.slot_base + sl) + c : -1;
+        }
+        S val[18];
+#pragma unroll
+        for (int t = 0; t < 18; ++t) val[t] = off[t] >= 0 ? __ldg(pose_inc + off[t]) : S(0);
+#pragma unroll
+        for (int t = 0; t < 18; ++t) {
+          const int e = base + lane + 32 * t;
+          if (off[t] >= 0) sP[e] = val[t];
+        }
+      }
+    }
+    __syncwarp();
+    // s_m = sum_c q1d[m][c] dp[c]   (ref: ipp:233-239)
     S sm[3] = {0, 0, 0};
     if (active) {
       for (int i = j; i < n; i += G) {
-        const size_t s = (size_t)(slot0 + i);
-        const S* dp = pose_inc + 9 * (size_t)D.slot_cam[s];
-        const S* rc = D.rec + 48 * s;
+        const int sl = g * n + i;
+        const S* q = sQ + 28 * sl;
+        const S* dp = sP + 9 * sl;
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
           const S d = dp[c];
-          sm[0] += rc[18 + c] * d; sm[1] += rc[27 + c] * d; sm[2] += rc[36 + c] * d;
+          sm[0] += q[c] * d; sm[1] += q[9 + c] * d; sm[2] += q[18 + c] * d;
         }
       }
     }
@@ -1455,20 +1629,21 @@ __global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* 
       inc[0] = -s0; inc[1] = -s1; inc[2] = -s2;
       jls[0] = lk[18]; jls[1] = lk[19]; jls[2] = lk[20];
     }
+    // model cost change in the un-rotated basis (ref: ipp:255-262, see header comment)
     S lpart = 0;
     if (active) {
       for (int i = j; i < n; i += G) {
-        const size_t s = (size_t)(slot0 + i);
-        const S* dp = pose_inc + 9 * (size_t)D.slot_cam[s];
-        const S* rc = D.rec + 48 * s;
-        const S* jl = D.jl + 6 * s;
+        const int sl = g * n + i;
+        const S* jq = sJ + 20 * sl;
+        const S* dp = sP + 9 * sl;
+        const S* jl = sL + 6 * sl;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           S ji = 0;
 #pragma unroll
-          for (int c = 0; c < 9; ++c) ji += rc[9 * rr + c] * dp[c];
+          for (int c = 0; c < 9; ++c) ji += jq[9 * rr + c] * dp[c];
           ji += jl[3 * rr] * inc[0] + jl[3 * rr + 1] * inc[1] + jl[3 * rr + 2] * inc[2];
-          lpart += ji * (S(0.5) * ji + D.res[2 * s + rr]);
+          lpart += ji * (S(0.5) * ji + sR[2 * sl + rr]);
         }
       }
     }
@@ -1482,6 +1657,7 @@ __global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* 
 #pragma unroll
       for (int d = 0; d < 3; ++d) pw[d] += inc[d] * jls[d];
     }
+    __syncwarp();
   }
   block_sum_store<1>(ld, partials);
 }

@@ -220,8 +220,9 @@ struct Solver : rba_handle {
     TRY(dalloc(&D.cams, (size_t)10 * nc)); TRY(dalloc(&cams_bk, (size_t)10 * nc));
     TRY(dalloc(&D.lms, (size_t)3 * L.nl_local)); TRY(dalloc(&lms_bk, (size_t)3 * L.nl_local));
     TRY(dalloc(&D.panel, (size_t)L.panel_scalars));
-    TRY(dalloc(&D.rec, (size_t)48 * L.nslots));
-    TRY(dalloc(&D.q1u, (size_t)27 * L.nslots));
+    TRY(dalloc(&D.jp, (size_t)20 * L.nslots));
+    TRY(dalloc(&D.q1u, (size_t)28 * L.nslots));
+    TRY(dalloc(&D.q1d, (size_t)28 * L.nslots));
     TRY(dalloc(&D.jl, (size_t)6 * L.nslots));
     TRY(dalloc(&D.res, (size_t)2 * L.nslots));
     TRY(dalloc(&D.lmk, (size_t)24 * L.sorted_lm.size()));
@@ -233,19 +234,35 @@ struct Solver : rba_handle {
     TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4));
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_state, 1));
-#undef TRY
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
     CU(cudaMallocHost((void**)&h_red, 8 * sizeof(double)));
     CU(cudaMallocHost((void**)&h_flags, 4 * sizeof(int)));
-    // shared-memory opt-in
-    k1_warps = 4;
-    while (k1_warps > 1 && (size_t)k1_warps * L.k1_scratch_per_warp * sizeof(S) > 200 * 1024) k1_warps >>= 1;
-    if ((size_t)k1_warps * L.k1_scratch_per_warp * sizeof(S) > 220 * 1024) {
-      g_err = "track length " + std::to_string(L.max_n) + " exceeds the shared-memory budget of the linearize+QR kernel";
-      return RBA_ERR_UNSUPPORTED;
+    // tile kernels (linearize+QR, stage 2, back-substitution): scratch in shared memory when the tile fits in
+    // TILE_CAP scalars per warp, else in a per-warp slice of a global buffer (very long tracks; slow but general)
+    {
+      long long need_max = 0;
+      for (const TileInfo& T : L.tiles) {
+        const int Wn = (32 / T.G) * T.n;
+        need_max = std::max<long long>(need_max, std::max({(long long)Wn * 60 + 64, (long long)stage2_need(T.n, T.G, T.KP), (long long)Wn * 68}));
+      }
+      tile_sc.smem_cap = TILE_CAP;
+      tile_sc.gbase = nullptr;
+      tile_sc.gstride = 0;
+      tile_smem = (size_t)TILE_WARPS * TILE_CAP * sizeof(S);
+      tile_blocks_per_sm = 2;
+      if (need_max > TILE_CAP) {
+        long long warps = (long long)sm_count * tile_blocks_per_sm * TILE_WARPS;
+        while (warps > TILE_WARPS && warps * need_max * (long long)sizeof(S) > (1LL << 31)) warps /= 2;
+        tile_max_blocks = (int)std::max<long long>(1, warps / TILE_WARPS);
+        tile_sc.gstride = (need_max + 3) & ~3LL;
+        TRY(dalloc(&tile_sc.gbase, (size_t)(tile_max_blocks * TILE_WARPS) * tile_sc.gstride, false));
+      } else {
+        tile_max_blocks = sm_count * tile_blocks_per_sm;
+      }
+      CU(cudaFuncSetAttribute(k_linearize_qr<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+      CU(cudaFuncSetAttribute(k_stage2<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+      CU(cudaFuncSetAttribute(k_back_substitute<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
     }
-    k1_smem = (size_t)k1_warps * L.k1_scratch_per_warp * sizeof(S);
-    CU(cudaFuncSetAttribute(k_linearize_qr<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k1_smem, 1024)));
     k4_smem_small = (size_t)K4_WARPS * L.k4_scratch_per_warp * sizeof(S);
     if (k4_smem_small > 200 * 1024) { g_err = "matvec scratch exceeds shared memory"; return RBA_ERR_UNSUPPORTED; }
     CU(cudaFuncSetAttribute(k_matvec_small<S, K4_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(k4_smem_small, 1024)));
@@ -278,14 +295,19 @@ struct Solver : rba_handle {
         if (const char* b = getenv("RBA_MATVEC_BLOCKS_PER_SM")) k4_tma_blocks_per_sm = std::max(1, atoi(b));
       }
     }
+#undef TRY
     CU(cudaStreamSynchronize(stream));
     return RBA_OK;
   }
   static constexpr int K4_WARPS = 4;
   static constexpr int K4_NS = 3;             // TMA ring stages per warp
   static constexpr int K4_STAGE = 4608;       // bytes per stage (2 rows of an f32 KP=9 tile)
-  int k1_warps = 4;
-  size_t k1_smem = 0, k4_smem_small = 0, k4_smem_tma = 0;
+  static constexpr int TILE_CAP = 6144;                        // scratch scalars per warp held in shared memory
+  static constexpr int TILE_WARPS = sizeof(S) == 4 ? 4 : 2;    // 96 KB of dynamic shared memory per block either way
+  Scratch<S> tile_sc{};
+  size_t tile_smem = 0;
+  int tile_blocks_per_sm = 2, tile_max_blocks = 296;
+  size_t k4_smem_small = 0, k4_smem_tma = 0;
   bool use_tma = true;
   int k4_tma_blocks_per_sm = 2;
 
@@ -340,6 +362,7 @@ struct Solver : rba_handle {
     return RBA_OK;
   }
 
+  int tile_grid() const { return std::max(1, std::min(tile_max_blocks, (D.ntiles + TILE_WARPS - 1) / TILE_WARPS)); }
   int grid_for(long long work_items, int per_block, int blocks_per_sm) const {
     long long g = (work_items + per_block - 1) / per_block;
     g = std::min<long long>(g, (long long)sm_count * blocks_per_sm);
@@ -387,7 +410,7 @@ struct Solver : rba_handle {
     rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.diag2, nullptr); if (rc) return rc;
     k_scaling<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.diag2, D.scaling, 9 * nc, (S)ko.jacobi_eps);
     // pass B: linearize (scaled) + Jl scaling + Householder QR + panel write
-    k_linearize_qr<S><<<grid_for(D.ntiles, k1_warps, 4), k1_warps * 32, k1_smem, stream>>>(D, ko, L.k1_scratch_per_warp, d_flags);
+    k_linearize_qr<S><<<tile_grid(), TILE_WARPS * 32, tile_smem, stream>>>(D, ko, tile_sc, d_flags);
     launches += 2;
     if (opt.preconditioner_type == 0) {
       // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)
@@ -409,7 +432,7 @@ struct Solver : rba_handle {
   }
 
   int precond_blocks(bool schur, S* dst) {
-    k_precond_partial<S><<<(n_pb_items + 127) / 128, 128, 0, stream>>>(D.rec, d_csr_obs_slots, d_pb_items, n_pb_items, schur ? 1 : 0, D.pblk);
+    k_precond_partial<S><<<(n_pb_items + 127) / 128, 128, 0, stream>>>(D.jp, D.q1d, d_csr_obs_slots, d_pb_items, n_pb_items, schur ? 1 : 0, D.pblk);
     k_precond_final<S><<<(45 * nc + 255) / 256, 256, 0, stream>>>(D.pblk, d_pb_item_ptr, nc, dst);
     launches += 2;
     return allreduce(dst, (size_t)81 * nc, false);
@@ -483,7 +506,7 @@ struct Solver : rba_handle {
     tm.matvec_launches = 0;
     int rc = start(ev_stage2); if (rc) return rc;
     // stage 2: landmark damping + gradient (+ SCHUR_JACOBI blocks)
-    k_stage2<S><<<grid_for(D.ntiles, 4, 8), 128, 0, stream>>>(D, lambda);
+    k_stage2<S><<<tile_grid(), TILE_WARPS * 32, tile_smem, stream>>>(D, lambda, tile_sc);
     ++launches;
     rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b, nullptr); if (rc) return rc;
     const bool schur = opt.preconditioner_type == 1;
@@ -559,8 +582,8 @@ struct Solver : rba_handle {
     else if (!have_inc) { g_err = "no device-resident increment"; return RBA_ERR_STATE; }
     int rc = start(ev_backsub); if (rc) return rc;
     CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
-    const int grid = std::min(grid_for(D.ntiles, 4, 8), EBLOCKS);
-    k_back_substitute<S><<<grid, 128, 0, stream>>>(D, D.inc, d_epart, d_flags);
+    const int grid = std::min(tile_grid(), EBLOCKS);
+    k_back_substitute<S><<<grid, TILE_WARPS * 32, tile_smem, stream>>>(D, D.inc, tile_sc, d_epart, d_flags);
     k_sum_partials<1><<<1, 256, 0, stream>>>(d_epart, grid, d_red);
     launches += 2;
     rc = allreduce(d_red, 1, true); if (rc) return rc;
@@ -667,16 +690,16 @@ struct Solver : rba_handle {
     const int pad = (4 - (9 * n) % 4) % 4, lm_idx = 9 * n + pad, res_idx = lm_idx + 3;
     if (rows != 2 * n + 3 || cols != res_idx + 1) { g_err = "block dims mismatch"; return RBA_ERR_INVALID_ARGUMENT; }
     CU(cudaStreamSynchronize(stream));
-    std::vector<S> panel((size_t)2 * n * KP * 64), rec((size_t)48 * n), lmk(24);
+    std::vector<S> panel((size_t)2 * n * KP * 64), rec((size_t)28 * n), lmk(24);
     const int slot0 = T.slot_base + g * n;
     CU(cudaMemcpy(panel.data(), D.panel + T.panel_off, panel.size() * sizeof(S), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(rec.data(), D.rec + (size_t)48 * slot0, rec.size() * sizeof(S), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rec.data(), D.q1d + (size_t)28 * slot0, rec.size() * sizeof(S), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(lmk.data(), D.lmk + (size_t)24 * sidx, 24 * sizeof(S), cudaMemcpyDeviceToHost));
     S* o = (S*)out;
     std::fill(o, o + (size_t)rows * cols, S(0));
     for (int c = 0; c < 9 * n; ++c) {
       const int i = c / 9, p = c % 9;
-      for (int m = 0; m < 3; ++m) o[(size_t)m * cols + c] = rec[(size_t)48 * i + 18 + 9 * m + p];  // damped Q1^T Jp
+      for (int m = 0; m < 3; ++m) o[(size_t)m * cols + c] = rec[(size_t)28 * i + 9 * m + p];  // damped Q1^T Jp
       const int pr = c / 2, v = c % 2, k = pr / G, j = pr % G, lane = g * G + j;
       for (int r = 0; r < 2 * n; ++r) o[(size_t)(3 + r) * cols + c] = panel[(((size_t)r * KP + k) * 32 + lane) * 2 + v];
     }
