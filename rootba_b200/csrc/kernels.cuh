@@ -410,6 +410,33 @@ __device__ __forceinline__ void warp_copy_out(S* __restrict__ dst, const S* __re
     for (int e = lane; e < count / 2; e += 32) d2[e] = s2[e];
   }
 }
+
+// ---- per-lane loads/stores of 16-byte aligned per-observation records (N scalars, N % 4 == 0) ----
+template <class S, int N>
+__device__ __forceinline__ void load_rec(const S* __restrict__ src, S (&v)[N]) {
+  if (sizeof(S) == 4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) { const float4 t = __ldg(s4 + q); v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+  } else {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q) { const double2 t = __ldg(s2 + q); v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+  }
+}
+template <class S, int N>
+__device__ __forceinline__ void store_rec(S* __restrict__ dst, const S (&v)[N]) {
+  if (sizeof(S) == 4) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+    double2* d2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q) d2[q] = make_double2(v[2 * q], v[2 * q + 1]);
+  }
+}
+
 // scratch of a tile kernel: shared memory when the tile fits, else a per-warp slice of a global buffer
 template <class S>
 struct Scratch {
@@ -717,9 +744,12 @@ __device__ __forceinline__ void rot_apply(const Rot<S>& g, S& x, S& y) {
 __host__ __device__ inline int stage2_need(int n, int G, int KP) {
   const int W = 32 / G, Wn = W * n;
   const int CS = (2 * G * KP) | 1;
-  return Wn * (28 + 20 + 2 + 9) + (G < 32 ? 3 * W * CS : 0) + W * 16;
+  return 3 * W * CS + Wn * 9 + W * 16 + 8;
 }
 
+// One warp per tile, one lane per observation: the 112-byte q1u / q1d and 80-byte jp records are moved with
+// 16-byte vector accesses straight from / to registers; only the 3 damping rows (which must land in the
+// column-interleaved panel layout) and the gradient are staged through shared memory for coalesced stores.
 template <class S>
 __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<S> sc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -731,18 +761,12 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
     const int n = T.n, G = T.G, KP = T.KP, W = 32 / G, Wn = W * n;
     const int ncols = 9 * n;
     const int CS = (2 * G * KP) | 1;
+    const int g = lane / G, j = lane - g * G;
+    const bool active = g < T.nvalid;
     S* ws = scratch_ptr(sc, ws_smem, stage2_need(n, G, KP));
-    S* sQ = ws;                 // [Wn][28]  q1u in, q1d out (in place)
-    S* sJ = sQ + Wn * 28;       // [Wn][20]  scaled pose Jacobian rows
-    S* sR = sJ + Wn * 20;       // [Wn][2]   weighted residual
-    S* sG = sR + Wn * 2;        // [Wn][9]   gradient contribution per observation
-    S* sRot = sG + Wn * 9;      // [W][16]   6 rotations (c,s) + damped Q1^T r (3)
-    S* sD = sRot + W * 16;      // [3][W][CS] damping rows in (landmark, column) order (G < 32 only)
-    const int nsl = T.nvalid * n;
-    // ---- coalesced loads of the tile's records ----
-    warp_copy_in(sQ, D.q1u + 28 * (size_t)T.slot_base, nsl * 28, lane);
-    warp_copy_in(sJ, D.jp + 20 * (size_t)T.slot_base, nsl * 20, lane);
-    for (int e = lane; e < nsl * 2; e += 32) sR[e] = D.res[2 * (size_t)T.slot_base + e];
+    S* sD = ws;                      // [3][W][CS] damping rows in (landmark, column) order
+    S* sG = sD + 3 * W * CS;         // [Wn][9]    gradient contribution per observation
+    S* sRot = sG + Wn * 9;           // [W][16]    6 rotations (c,s) + damped Q1^T r (3)
     // ---- rotations of landmark `lane` (ref: ipp:188-209), Eigen makeGivens / applyOnTheLeft ----
     if (lane < T.nvalid) {
       S* lk = D.lmk + 24 * (size_t)(T.lm_base + lane);
@@ -775,55 +799,53 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
       lk[15] = rr[0]; lk[16] = rr[1]; lk[17] = rr[2];
     }
     __syncwarp();
-    // ---- per column (observation-major order): q1d, damping rows, gradient ----
-    V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off);
-    S* prow = D.panel + T.panel_off + (size_t)(2 * n - 3) * KP * 64;  // first damping row
-    {
-      int g2 = 0, c = lane;
-      while (c >= ncols) { c -= ncols; ++g2; }
-      while (g2 < T.nvalid) {
-        const int i = c / 9, p = c - 9 * i;
-        const int sl = g2 * n + i;
-        const S* ro = sRot + 16 * g2;
-        S* q = sQ + 28 * sl + p;
-        S qv[3] = {q[0], q[9], q[18]}, dv[3] = {0, 0, 0};
-        int qi = 0;
+    // ---- one observation per lane and step: q1d, damping-row entries, gradient ----
+    if (active) {
+      Rot<S> rot[6];
+      const S* ro = sRot + 16 * g;
 #pragma unroll
-        for (int nn = 0; nn < 3; ++nn)
+      for (int q = 0; q < 6; ++q) { rot[q].c = ro[2 * q]; rot[q].s = ro[2 * q + 1]; }
+      const S rr0 = ro[12], rr1 = ro[13], rr2 = ro[14];
+      for (int i = j; i < n; i += G) {
+        const size_t sl = (size_t)(T.slot_base + g * n + i);
+        S q[28], jp[20];
+        load_rec<S, 28>(D.q1u + 28 * sl, q);
+        load_rec<S, 20>(D.jp + 20 * sl, jp);
+        const S r0 = D.res[2 * sl], r1 = D.res[2 * sl + 1];
+        S* d0 = sD + (0 * W + g) * CS + 9 * i;
+        S* d1 = sD + (1 * W + g) * CS + 9 * i;
+        S* d2 = sD + (2 * W + g) * CS + 9 * i;
+        S* go = sG + 9 * (g * n + i);
 #pragma unroll
-          for (int m = 0; m <= nn; ++m) {
-            Rot<S> gq; gq.c = ro[2 * qi]; gq.s = ro[2 * qi + 1]; ++qi;
-            rot_apply(gq, dv[nn - m], qv[nn]);
-          }
-        q[0] = qv[0]; q[9] = qv[1]; q[18] = qv[2];
-        // gradient of the reduced system: b_c = jp_c^T r_i - q1d_c^T (Q1^T r)_d
-        sG[9 * sl + p] = sJ[20 * sl + p] * sR[2 * sl] + sJ[20 * sl + 9 + p] * sR[2 * sl + 1] -
-                         (qv[0] * ro[12] + qv[1] * ro[13] + qv[2] * ro[14]);
-        if (G == 32) {
-          // W = 1: the panel row layout [k][lane][2] is the natural column order
+        for (int p = 0; p < 9; ++p) {
+          S qv[3] = {q[p], q[9 + p], q[18 + p]}, dv[3] = {0, 0, 0};
+          int qi = 0;
 #pragma unroll
-          for (int d = 0; d < 3; ++d) prow[(size_t)d * KP * 64 + c] = dv[d];
-        } else {
+          for (int nn = 0; nn < 3; ++nn)
 #pragma unroll
-          for (int d = 0; d < 3; ++d) sD[(d * W + g2) * CS + c] = dv[d];
+            for (int m = 0; m <= nn; ++m) rot_apply(rot[qi++], dv[nn - m], qv[nn]);
+          q[p] = qv[0]; q[9 + p] = qv[1]; q[18 + p] = qv[2];
+          d0[p] = dv[0]; d1[p] = dv[1]; d2[p] = dv[2];
+          // gradient of the reduced system: b_c = jp_c^T r_i - q1d_c^T (Q1^T r)_d
+          go[p] = jp[p] * r0 + jp[9 + p] * r1 - (qv[0] * rr0 + qv[1] * rr1 + qv[2] * rr2);
         }
-        c += 32;
-        while (c >= ncols) { c -= ncols; ++g2; }
+        q[27] = 0;
+        store_rec<S, 28>(D.q1d + 28 * sl, q);
       }
     }
     __syncwarp();
-    // ---- coalesced stores ----
-    warp_copy_out(D.q1d + 28 * (size_t)T.slot_base, sQ, nsl * 28, lane);
-    for (int e = lane; e < nsl * 9; e += 32) D.yobs[9 * (size_t)T.slot_base + e] = sG[e];
-    if (G < 32) {
-      const int g = lane / G, j = lane - g * G;
-      if (g < T.nvalid) {
+    // ---- coalesced stores: gradient (observation-major), damping rows (panel layout) ----
+    {
+      const int nsl = T.nvalid * n;
+      for (int e = lane; e < nsl * 9; e += 32) D.yobs[9 * (size_t)T.slot_base + e] = sG[e];
+      if (active) {
+        V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off) + (size_t)(2 * n - 3) * KP * 32 + lane;
         for (int k = 0; k < KP; ++k) {
           const int c = 2 * j + 2 * G * k;
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             const S* row = sD + (d * W + g) * CS;
-            ptile[((size_t)(2 * n - 3 + d) * KP + k) * 32 + lane] = mk2(c < ncols ? row[c] : S(0), c + 1 < ncols ? row[c + 1] : S(0));
+            ptile[((size_t)d * KP + k) * 32] = mk2(c < ncols ? row[c] : S(0), c + 1 < ncols ? row[c + 1] : S(0));
           }
         }
       }
@@ -1558,60 +1580,32 @@ __global__ void __launch_bounds__(512) k_pcg_vec(DevPtrs<S> D, PcgState* st, con
 // K6  back-substitution (ref: ipp:212-284).  Model-cost change evaluated in the un-rotated basis:
 //     Q^T (Jp dp + Jl inc) has the same norm / inner product with Q^T r as (Jp dp + Jl inc) with r.
 // ------------------------------------------------------------------------------------------------
+// One warp per tile, one lane per observation, no shared memory: every record is one or a few 16-byte loads.
+// Pass 1 (q1d, dp) gives s_m and the landmark increment, pass 2 (jp, jl, r, dp) the model cost change.
 template <class S>
-__global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* __restrict__ pose_inc, Scratch<S> sc,
+__global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* __restrict__ pose_inc,
                                                           double* partials, int* bad_flag) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  S* ws_smem = reinterpret_cast<S*>(smem_raw) + (size_t)wib * sc.smem_cap;
   double ld[1] = {0};
   for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
     const TileInfo T = D.tiles[t];
-    const int n = T.n, G = T.G, W = 32 / G, Wn = W * n;
+    const int n = T.n, G = T.G;
     const int g = lane / G, j = lane - g * G;
     const bool active = g < T.nvalid;
     const int sidx = T.lm_base + g;
-    const int nsl = T.nvalid * n;
-    S* ws = scratch_ptr(sc, ws_smem, Wn * 68);
-    S* sQ = ws;              // [Wn][28] damped Q1^T Jp
-    S* sJ = sQ + Wn * 28;    // [Wn][20] scaled pose Jacobian rows
-    S* sL = sJ + Wn * 20;    // [Wn][6]  scaled landmark Jacobian rows
-    S* sR = sL + Wn * 6;     // [Wn][2]  weighted residual
-    S* sP = sR + Wn * 2;     // [Wn][9]  gathered pose increment (+3 spare)
-    warp_copy_in(sQ, D.q1d + 28 * (size_t)T.slot_base, nsl * 28, lane);
-    warp_copy_in(sJ, D.jp + 20 * (size_t)T.slot_base, nsl * 20, lane);
-    for (int e = lane; e < nsl * 6; e += 32) sL[e] = D.jl[6 * (size_t)T.slot_base + e];
-    for (int e = lane; e < nsl * 2; e += 32) sR[e] = D.res[2 * (size_t)T.slot_base + e];
-    {  // gather of the pose increments: index loads first, then the dependent loads (two round trips per 18*32 entries)
-      for (int base = 0; base < nsl * 9; base += 18 * 32) {
-        int off[18];
-#pragma unroll
-        for (int t = 0; t < 18; ++t) {
-          const int e = base + lane + 32 * t;
-          const int sl = e / 9, c = e - 9 * sl;
-          off[t] = e < nsl * 9 ? 9 * __ldg(D.slot_cam + T.slot_base + sl) + c : -1;
-        }
-        S val[18];
-#pragma unroll
-        for (int t = 0; t < 18; ++t) val[t] = off[t] >= 0 ? __ldg(pose_inc + off[t]) : S(0);
-#pragma unroll
-        for (int t = 0; t < 18; ++t) {
-          const int e = base + lane + 32 * t;
-          if (off[t] >= 0) sP[e] = val[t];
-        }
-      }
-    }
-    __syncwarp();
-    // s_m = sum_c q1d[m][c] dp[c]   (ref: ipp:233-239)
+    const size_t slot0 = (size_t)(T.slot_base + g * n);
+    // ---- pass 1: s_m = sum_c q1d[m][c] dp[c]   (ref: ipp:233-239) ----
     S sm[3] = {0, 0, 0};
     if (active) {
+#pragma unroll 2
       for (int i = j; i < n; i += G) {
-        const int sl = g * n + i;
-        const S* q = sQ + 28 * sl;
-        const S* dp = sP + 9 * sl;
+        const size_t sl = slot0 + i;
+        const S* dp = pose_inc + 9 * (size_t)__ldg(D.slot_cam + sl);
+        S q[28];
+        load_rec<S, 28>(D.q1d + 28 * sl, q);
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
-          const S d = dp[c];
+          const S d = __ldg(dp + c);
           sm[0] += q[c] * d; sm[1] += q[9 + c] * d; sm[2] += q[18 + c] * d;
         }
       }
@@ -1629,21 +1623,25 @@ __global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* 
       inc[0] = -s0; inc[1] = -s1; inc[2] = -s2;
       jls[0] = lk[18]; jls[1] = lk[19]; jls[2] = lk[20];
     }
-    // model cost change in the un-rotated basis (ref: ipp:255-262, see header comment)
+    // ---- pass 2: model cost change in the un-rotated basis (ref: ipp:255-262, see header comment) ----
     S lpart = 0;
     if (active) {
+#pragma unroll 2
       for (int i = j; i < n; i += G) {
-        const int sl = g * n + i;
-        const S* jq = sJ + 20 * sl;
-        const S* dp = sP + 9 * sl;
-        const S* jl = sL + 6 * sl;
+        const size_t sl = slot0 + i;
+        const S* dp = pose_inc + 9 * (size_t)__ldg(D.slot_cam + sl);
+        S jp[20], dv[9];
+        load_rec<S, 20>(D.jp + 20 * sl, jp);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) dv[c] = __ldg(dp + c);
+        const S* jl = D.jl + 6 * sl;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           S ji = 0;
 #pragma unroll
-          for (int c = 0; c < 9; ++c) ji += jq[9 * rr + c] * dp[c];
+          for (int c = 0; c < 9; ++c) ji += jp[9 * rr + c] * dv[c];
           ji += jl[3 * rr] * inc[0] + jl[3 * rr + 1] * inc[1] + jl[3 * rr + 2] * inc[2];
-          lpart += ji * (S(0.5) * ji + sR[2 * sl + rr]);
+          lpart += ji * (S(0.5) * ji + D.res[2 * sl + rr]);
         }
       }
     }
@@ -1657,7 +1655,6 @@ __global__ void __launch_bounds__(128) k_back_substitute(DevPtrs<S> D, const S* 
 #pragma unroll
       for (int d = 0; d < 3; ++d) pw[d] += inc[d] * jls[d];
     }
-    __syncwarp();
   }
   block_sum_store<1>(ld, partials);
 }

@@ -237,31 +237,34 @@ struct Solver : rba_handle {
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
     CU(cudaMallocHost((void**)&h_red, 8 * sizeof(double)));
     CU(cudaMallocHost((void**)&h_flags, 4 * sizeof(int)));
-    // tile kernels (linearize+QR, stage 2, back-substitution): scratch in shared memory when the tile fits in
-    // TILE_CAP scalars per warp, else in a per-warp slice of a global buffer (very long tracks; slow but general)
+    // tile kernels (linearize+QR, stage 2): scratch in shared memory when the tile fits in the kernel's cap (scalars per
+    // warp), else in a per-warp slice of a global buffer (very long tracks; slow but general)
     {
-      long long need_max = 0;
+      long long need1 = 0, need2 = 0;
       for (const TileInfo& T : L.tiles) {
         const int Wn = (32 / T.G) * T.n;
-        need_max = std::max<long long>(need_max, std::max({(long long)Wn * 60 + 64, (long long)stage2_need(T.n, T.G, T.KP), (long long)Wn * 68}));
+        need1 = std::max<long long>(need1, (long long)Wn * 60 + 64);
+        need2 = std::max<long long>(need2, (long long)stage2_need(T.n, T.G, T.KP));
       }
-      tile_sc.smem_cap = TILE_CAP;
-      tile_sc.gbase = nullptr;
-      tile_sc.gstride = 0;
-      tile_smem = (size_t)TILE_WARPS * TILE_CAP * sizeof(S);
-      tile_blocks_per_sm = 2;
-      if (need_max > TILE_CAP) {
-        long long warps = (long long)sm_count * tile_blocks_per_sm * TILE_WARPS;
-        while (warps > TILE_WARPS && warps * need_max * (long long)sizeof(S) > (1LL << 31)) warps /= 2;
-        tile_max_blocks = (int)std::max<long long>(1, warps / TILE_WARPS);
-        tile_sc.gstride = (need_max + 3) & ~3LL;
-        TRY(dalloc(&tile_sc.gbase, (size_t)(tile_max_blocks * TILE_WARPS) * tile_sc.gstride, false));
-      } else {
-        tile_max_blocks = sm_count * tile_blocks_per_sm;
-      }
-      CU(cudaFuncSetAttribute(k_linearize_qr<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-      CU(cudaFuncSetAttribute(k_stage2<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-      CU(cudaFuncSetAttribute(k_back_substitute<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+      auto setup = [&](Scratch<S>& sc, int cap, long long need, size_t& smem, int& blocks_per_sm, int& max_blocks) -> int {
+        sc.smem_cap = cap; sc.gbase = nullptr; sc.gstride = 0;
+        smem = (size_t)TILE_WARPS * cap * sizeof(S);
+        blocks_per_sm = std::max(1, (int)((220 * 1024) / (smem + 1024)));
+        max_blocks = sm_count * blocks_per_sm;
+        if (need > cap) {
+          long long warps = (long long)max_blocks * TILE_WARPS;
+          while (warps > TILE_WARPS && warps * need * (long long)sizeof(S) > (1LL << 30)) warps /= 2;
+          max_blocks = (int)std::max<long long>(1, warps / TILE_WARPS);
+          sc.gstride = (need + 3) & ~3LL;
+          int rc2 = dalloc(&sc.gbase, (size_t)(max_blocks * TILE_WARPS) * sc.gstride, false);
+          if (rc2) return rc2;
+        }
+        return RBA_OK;
+      };
+      TRY(setup(k1_sc, K1_CAP, need1, k1_smem, k1_bps, k1_max_blocks));
+      TRY(setup(k2_sc, K2_CAP, need2, k2_smem, k2_bps, k2_max_blocks));
+      CU(cudaFuncSetAttribute(k_linearize_qr<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
+      CU(cudaFuncSetAttribute(k_stage2<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
     }
     k4_smem_small = (size_t)K4_WARPS * L.k4_scratch_per_warp * sizeof(S);
     if (k4_smem_small > 200 * 1024) { g_err = "matvec scratch exceeds shared memory"; return RBA_ERR_UNSUPPORTED; }
@@ -302,11 +305,12 @@ struct Solver : rba_handle {
   static constexpr int K4_WARPS = 4;
   static constexpr int K4_NS = 3;             // TMA ring stages per warp
   static constexpr int K4_STAGE = 4608;       // bytes per stage (2 rows of an f32 KP=9 tile)
-  static constexpr int TILE_CAP = 6144;                        // scratch scalars per warp held in shared memory
-  static constexpr int TILE_WARPS = sizeof(S) == 4 ? 4 : 2;    // 96 KB of dynamic shared memory per block either way
-  Scratch<S> tile_sc{};
-  size_t tile_smem = 0;
-  int tile_blocks_per_sm = 2, tile_max_blocks = 296;
+  static constexpr int TILE_WARPS = 4;
+  static constexpr int K1_CAP = 3904;   // scalars of shared memory per warp: linearize+QR needs 60 * W * n + 64 (= 3904 for the standard tiles)
+  static constexpr int K2_CAP = 2944;   // stage 2 needs 3 * W * CS + 9 * W * n + 16 W + 8 (<= 2944 for the standard tiles)
+  Scratch<S> k1_sc{}, k2_sc{};
+  size_t k1_smem = 0, k2_smem = 0;
+  int k1_bps = 2, k2_bps = 2, k1_max_blocks = 296, k2_max_blocks = 296;
   size_t k4_smem_small = 0, k4_smem_tma = 0;
   bool use_tma = true;
   int k4_tma_blocks_per_sm = 2;
@@ -362,7 +366,7 @@ struct Solver : rba_handle {
     return RBA_OK;
   }
 
-  int tile_grid() const { return std::max(1, std::min(tile_max_blocks, (D.ntiles + TILE_WARPS - 1) / TILE_WARPS)); }
+  int tile_grid(int max_blocks) const { return std::max(1, std::min(max_blocks, (D.ntiles + TILE_WARPS - 1) / TILE_WARPS)); }
   int grid_for(long long work_items, int per_block, int blocks_per_sm) const {
     long long g = (work_items + per_block - 1) / per_block;
     g = std::min<long long>(g, (long long)sm_count * blocks_per_sm);
@@ -410,7 +414,7 @@ struct Solver : rba_handle {
     rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.diag2, nullptr); if (rc) return rc;
     k_scaling<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.diag2, D.scaling, 9 * nc, (S)ko.jacobi_eps);
     // pass B: linearize (scaled) + Jl scaling + Householder QR + panel write
-    k_linearize_qr<S><<<tile_grid(), TILE_WARPS * 32, tile_smem, stream>>>(D, ko, tile_sc, d_flags);
+    k_linearize_qr<S><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags);
     launches += 2;
     if (opt.preconditioner_type == 0) {
       // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)
@@ -506,7 +510,7 @@ struct Solver : rba_handle {
     tm.matvec_launches = 0;
     int rc = start(ev_stage2); if (rc) return rc;
     // stage 2: landmark damping + gradient (+ SCHUR_JACOBI blocks)
-    k_stage2<S><<<tile_grid(), TILE_WARPS * 32, tile_smem, stream>>>(D, lambda, tile_sc);
+    k_stage2<S><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc);
     ++launches;
     rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b, nullptr); if (rc) return rc;
     const bool schur = opt.preconditioner_type == 1;
@@ -582,8 +586,8 @@ struct Solver : rba_handle {
     else if (!have_inc) { g_err = "no device-resident increment"; return RBA_ERR_STATE; }
     int rc = start(ev_backsub); if (rc) return rc;
     CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
-    const int grid = std::min(tile_grid(), EBLOCKS);
-    k_back_substitute<S><<<grid, TILE_WARPS * 32, tile_smem, stream>>>(D, D.inc, tile_sc, d_epart, d_flags);
+    const int grid = std::min(tile_grid(sm_count * 4), EBLOCKS);
+    k_back_substitute<S><<<grid, TILE_WARPS * 32, 0, stream>>>(D, D.inc, d_epart, d_flags);
     k_sum_partials<1><<<1, 256, 0, stream>>>(d_epart, grid, d_red);
     launches += 2;
     rc = allreduce(d_red, 1, true); if (rc) return rc;

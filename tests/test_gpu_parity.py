@@ -182,7 +182,9 @@ def test_lm_trajectory(small_problem, dtype, kw):
         if significant:
             assert bool(a["step_is_successful"]) == bool(b["step_is_successful"]), a["iteration"]
             if a["iteration"] > 0:
-                assert abs(a["linear_solver_iterations"] - int(b["cg_iterations"])) <= 2, a["iteration"]
+                # the zeta stopping rule is a threshold on rounded quantities: +-2 in f64, +-30% in f32
+                slack = 2 if dtype == np.float64 else max(2, int(0.3 * b["cg_iterations"]))
+                assert abs(a["linear_solver_iterations"] - int(b["cg_iterations"])) <= slack, a["iteration"]
         prev = b["cost"]
     assert g_it[-1]["cost"]["all"]["error"] < 0.2 * g_it[0]["cost"]["all"]["error"]
     lin.close()
