@@ -1,0 +1,77 @@
+// bal_qr: square-root BA solver on a BAL file with the GPU linearizor (counterpart of src/app/bal_qr.cpp:44-115).
+//   bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI]
+//          [--residual-robust-norm NONE|HUBER] [--residual-huber-parameter X] [--no-normalize] [--dump-problem out.bin]
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "solver.hpp"
+
+using namespace rootba_b200;
+
+template <class S>
+int run(const std::string& input, bool normalize, const SolverOptions& o, const std::string& log_path) {
+  auto problem = load_normalized_bal_problem<S>(input, normalize);
+  std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s'\n", problem.num_cameras(), problem.num_landmarks(),
+              (long long)problem.num_observations(), input.c_str());
+  SolverSummary summary;
+  bundle_adjust_manual<S>(problem, o, &summary);
+  std::ofstream f(log_path);  // minimal ba_log.json (bal/ba_log.hpp:139-237: per-iteration costs and timings)
+  f << "{\n  \"_solver_summary\": {\"solver_type\": \"bal_qr_b200\", \"termination_type\": \"" << summary.termination_type << "\", \"message\": \""
+    << summary.message << "\"},\n  \"_iterations\": [\n";
+  for (size_t i = 0; i < summary.iterations.size(); ++i) {
+    const auto& it = summary.iterations[i];
+    f << "    {\"iteration\": " << it.iteration << ", \"cost\": " << it.cost.all.error << ", \"cost_valid\": " << it.cost.valid.error
+      << ", \"step_is_successful\": " << (it.step_is_successful ? "true" : "false") << ", \"linear_solver_iterations\": " << it.linear_solver_iterations
+      << ", \"stage1_time_in_seconds\": " << it.stage1_time_in_seconds << ", \"stage2_time_in_seconds\": " << it.stage2_time_in_seconds
+      << ", \"solve_reduced_system_time_in_seconds\": " << it.solve_reduced_system_time_in_seconds
+      << ", \"back_substitution_time_in_seconds\": " << it.back_substitution_time_in_seconds << "}" << (i + 1 < summary.iterations.size() ? "," : "") << "\n";
+  }
+  f << "  ]\n}\n";
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  std::string input, dump, log_path = "ba_log.json";
+  bool use_double = true, normalize = true;
+  SolverOptions o;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto next = [&]() -> std::string { if (i + 1 >= argc) { std::cerr << "missing value for " << a << "\n"; std::exit(2); } return argv[++i]; };
+    if (a == "--input") input = next();
+    else if (a == "--no-use-double") use_double = false;
+    else if (a == "--use-double") use_double = true;
+    else if (a == "--no-normalize") normalize = false;
+    else if (a == "--max-num-iterations") o.max_num_iterations = std::stoi(next());
+    else if (a == "--max-linear-solver-iterations") o.max_linear_solver_iterations = std::stoi(next());
+    else if (a == "--eta") o.eta = std::stod(next());
+    else if (a == "--function-tolerance") o.function_tolerance = std::stod(next());
+    else if (a == "--preconditioner-type") { const std::string v = next(); o.preconditioner_type = v == "JACOBI" ? SolverOptions::PreconditionerType::JACOBI : SolverOptions::PreconditionerType::SCHUR_JACOBI; }
+    else if (a == "--residual-robust-norm") { const std::string v = next(); o.robust_norm = v == "HUBER" ? SolverOptions::RobustNorm::HUBER : SolverOptions::RobustNorm::NONE; }
+    else if (a == "--residual-huber-parameter") o.huber_parameter = std::stod(next());
+    else if (a == "--optimized-cost") { const std::string v = next(); o.optimized_cost = v == "ERROR" ? SolverOptions::OptimizedCost::ERROR : v == "ERROR_VALID" ? SolverOptions::OptimizedCost::ERROR_VALID : SolverOptions::OptimizedCost::ERROR_VALID_AVG; }
+    else if (a == "--log-path") log_path = next();
+    else if (a == "--dump-problem") dump = next();
+    else if (a == "--help" || a == "-h") { std::cout << "usage: bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI] ...\n"; return 0; }
+    else { std::cerr << "unknown option " << a << "\n"; return 2; }
+  }
+  if (input.empty()) { std::cerr << "--input is required\n"; return 2; }
+  try {
+    if (!dump.empty()) {  // loader check (host only, no GPU): normalised double arrays in SoA form
+      auto p = load_normalized_bal_problem<double>(input, normalize);
+      std::vector<int64_t> off; std::vector<int32_t> oc; std::vector<double> xy, c, l;
+      p.export_topology(off, oc, xy); p.export_state(c, l);
+      std::ofstream f(dump, std::ios::binary);
+      const int64_t hdr[3] = {p.num_cameras(), p.num_landmarks(), (int64_t)oc.size()};
+      f.write((const char*)hdr, sizeof(hdr));
+      f.write((const char*)c.data(), c.size() * 8); f.write((const char*)l.data(), l.size() * 8);
+      f.write((const char*)off.data(), off.size() * 8); f.write((const char*)oc.data(), oc.size() * 4); f.write((const char*)xy.data(), xy.size() * 8);
+      return 0;
+    }
+    o.use_double = use_double;
+    return use_double ? run<double>(input, normalize, o, log_path) : run<float>(input, normalize, o, log_path);
+  } catch (const std::exception& e) {
+    std::cerr << "FATAL: " << e.what() << "\n";
+    return 1;
+  }
+}

@@ -1,0 +1,86 @@
+"""C++ host mirror (rootba_b200/host): BAL loader + normalisation vs the oracle's loader and the generator;
+bal_qr end-to-end on the GPU vs the Python host mirror."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_err
+
+BAL_QR = os.path.join(ROOT, "rootba_b200", "host", "bal_qr")
+
+
+def _build():
+    from rootba_b200 import _lib
+    _lib.build()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "rootba_b200", "host"), "-s"])
+
+
+def _read_dump(path):
+    raw = open(path, "rb").read()
+    nc, nl, nobs = np.frombuffer(raw, np.int64, 3)
+    o = 24
+    cams = np.frombuffer(raw, np.float64, 10 * nc, o).reshape(nc, 10); o += 80 * nc
+    lms = np.frombuffer(raw, np.float64, 3 * nl, o).reshape(nl, 3); o += 24 * nl
+    off = np.frombuffer(raw, np.int64, nl + 1, o); o += 8 * (nl + 1)
+    oc = np.frombuffer(raw, np.int32, nobs, o); o += 4 * nobs
+    xy = np.frombuffer(raw, np.float64, 2 * nobs, o).reshape(nobs, 2)
+    return cams, lms, off, oc, xy
+
+
+def test_loader_matches_oracle_and_generator(tmp_path):
+    from oracle import oracle_py as orc
+    from rootba_b200.synthetic import synth_bal, write_bal
+    _build()
+    prob = synth_bal(7, 60, 3.2, seed=5, normalize_scale=None, perturb_lm=0, perturb_rot=0, perturb_trans=0)
+    path = str(tmp_path / "p.txt")
+    write_bal(prob, path)
+    # raw load (no normalisation): round trip of the generator's arrays through the BAL text format
+    subprocess.check_call([BAL_QR, "--input", path, "--no-normalize", "--dump-problem", str(tmp_path / "raw.bin")])
+    cams, lms, off, oc, xy = _read_dump(str(tmp_path / "raw.bin"))
+    assert np.array_equal(off, prob.lm_off) and np.array_equal(oc, prob.obs_cam)  # indexing bit-exact
+    assert np.allclose(xy, prob.obs_xy, rtol=0, atol=1e-12) and np.allclose(lms, prob.lms, rtol=0, atol=1e-12)
+    q_sign = np.sign(np.sum(cams[:, :4] * prob.cams[:, :4], axis=1, keepdims=True))  # q and -q are the same rotation
+    assert np.allclose(cams[:, :4] * q_sign, prob.cams[:, :4], atol=1e-12)
+    assert np.allclose(cams[:, 4:], prob.cams[:, 4:], atol=1e-10)
+    # normalised load: two independent implementations (C++ host, oracle) of bal_problem.cpp:189-282,428-469
+    subprocess.check_call([BAL_QR, "--input", path, "--dump-problem", str(tmp_path / "norm.bin")])
+    cams, lms, off, oc, xy = _read_dump(str(tmp_path / "norm.bin"))
+    ref = orc.load_bal(path, normalize=True)
+    assert np.array_equal(off, ref["lm_off"]) and np.array_equal(oc, ref["obs_cam"])
+    assert rel_err(cams, ref["cams"]) < 1e-14 and rel_err(lms, ref["lms"]) < 1e-14 and np.array_equal(xy, ref["obs_xy"])
+
+
+def test_rejects_duplicate_observation(tmp_path):
+    _build()
+    p = tmp_path / "dup.txt"
+    p.write_text("1 1 2\n0 0 1.0 2.0\n0 0 1.5 2.5\n" + "0\n" * 9 + "0\n0\n1\n")
+    r = subprocess.run([BAL_QR, "--input", str(p), "--dump-problem", str(tmp_path / "x.bin")], capture_output=True)
+    assert r.returncode != 0  # the reference CHECK-fails on a duplicate (cam, lm) pair (bal_problem.cpp:229-230)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_double", [True, False])
+def test_bal_qr_matches_python_host(tmp_path, use_double):
+    import rootba_b200 as rb
+    from oracle import oracle_py as orc
+    from rootba_b200.synthetic import BalArrays, synth_bal, write_bal
+    _build()
+    prob = synth_bal(20, 400, 4.0, seed=9, normalize_scale=None)
+    path = str(tmp_path / "p.txt")
+    write_bal(prob, path)
+    log = str(tmp_path / "ba_log.json")
+    args = [BAL_QR, "--input", path, "--max-num-iterations", "4", "--log-path", log] + ([] if use_double else ["--no-use-double"])
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    its = json.load(open(log))["_iterations"]
+    d = orc.load_bal(path, normalize=True)
+    arrays = BalArrays(d["cams"], d["lms"], d["lm_off"], d["obs_cam"], d["obs_xy"])
+    dtype = np.float64 if use_double else np.float32
+    bp = rb.BalProblem.from_arrays(arrays, dtype)
+    summ = rb.bundle_adjust_manual(bp, rb.SolverOptions(max_num_iterations=4))
+    assert len(its) == len(summ["iterations"])
+    for a, b in zip(its, summ["iterations"]):
+        cb = b["cost"]["all"]["error"]
+        assert abs(a["cost"] - cb) <= (1e-9 if use_double else 2e-3) * cb + 1e-12 * its[0]["cost"]
