@@ -16,7 +16,8 @@ int run(const std::string& input, bool normalize, const SolverOptions& o, const 
               (long long)problem.num_observations(), input.c_str());
   SolverSummary summary;
   bundle_adjust_manual<S>(problem, o, &summary);
-  std::ofstream f(log_path);  // minimal ba_log.json (bal/ba_log.hpp:139-237: per-iteration costs and timings)
+  std::ofstream f(log_path);  // minimal ba_log.json
+  f.precision(17);  // (bal/ba_log.hpp:139-237: per-iteration costs and timings)
   f << "{\n  \"_solver_summary\": {\"solver_type\": \"bal_qr_b200\", \"termination_type\": \"" << summary.termination_type << "\", \"message\": \""
     << summary.message << "\"},\n  \"_iterations\": [\n";
   for (size_t i = 0; i < summary.iterations.size(); ++i) {
