@@ -321,15 +321,19 @@ __global__ void __launch_bounds__(256) k_jp_norms(DevPtrs<S> D, KOpts o, int* ba
 // of 32.  The slot indices are first staged in shared memory with coalesced loads (one round trip), then the value loads
 // are issued 16 deep, so an item costs ~1 + SEG_LEN/48 round trips instead of 2 * SEG_LEN/32.
 template <class S>
-__device__ __forceinline__ void cam_reduce_item(const S* __restrict__ src, const int* __restrict__ slots, const ReduceItem& I,
-                                                int lane, S* __restrict__ out9, int* sidx /* [SEG_LEN] per warp */) {
+__device__ __forceinline__ void cam_stage_indices(const int* __restrict__ slots, const ReduceItem& I, int lane, int* sidx) {
   const int cnt = I.end - I.begin;
 #pragma unroll
-  for (int t = 0; t < SEG_LEN / 32; ++t) {
+  for (int t = 0; t < (SEG_LEN + 31) / 32; ++t) {
     const int e = lane + 32 * t;
     if (e < cnt) sidx[e] = __ldg(slots + I.begin + e);
   }
   __syncwarp();
+}
+template <class S>
+__device__ __forceinline__ void cam_sum_staged(const S* __restrict__ src, const ReduceItem& I, int lane, S* __restrict__ out9,
+                                               const int* sidx) {
+  const int cnt = I.end - I.begin;
   const int s3 = lane / 9, c = lane - 9 * s3;
   const bool on = lane < 27;
   S acc = 0;
@@ -349,6 +353,12 @@ __device__ __forceinline__ void cam_reduce_item(const S* __restrict__ src, const
   const S a2 = __shfl_sync(0xffffffffu, acc, (lane + 18) & 31);
   if (lane < 9) out9[lane] = acc + a1 + a2;
 }
+template <class S>
+__device__ __forceinline__ void cam_reduce_item(const S* __restrict__ src, const int* __restrict__ slots, const ReduceItem& I,
+                                                int lane, S* __restrict__ out9, int* sidx /* [SEG_LEN] per warp */) {
+  cam_stage_indices<S>(slots, I, lane, sidx);
+  cam_sum_staged(src, I, lane, out9, sidx);
+}
 
 template <class S>
 __global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, const int* __restrict__ slots,
@@ -360,6 +370,48 @@ __global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, c
   const int wpb = blockDim.x >> 5;
   for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb)
     cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+}
+
+// Same, and the warp that completes the LAST segment of a camera (arrival counter) adds the camera's segment sums in
+// their fixed order and writes y[cam][9]: the result is complete when the kernel ends, deterministic, and needs no
+// second kernel.  cam_cnt must be zero on entry and is left zero.
+template <class S>
+__global__ void __launch_bounds__(256) k_cam_reduce_final(const S* __restrict__ src, const int* __restrict__ slots,
+                                                           const ReduceItem* __restrict__ items, int nitems,
+                                                           const int* __restrict__ cam_item_ptr, S* __restrict__ partial,
+                                                           int* cam_cnt, S* __restrict__ y, const int* done, int pdl) {
+  __shared__ int sidx_all[8][SEG_LEN];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  // the slot indices are constant: stage the first item's before the grid dependency is awaited
+  const int it0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  if (it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (done && *done) return;
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int it = it0; it < nitems; it += gridDim.x * wpb) {
+    const ReduceItem I = items[it];
+    if (it != it0) cam_stage_indices<S>(slots, I, lane, sidx_all[threadIdx.x >> 5]);
+    cam_sum_staged(src, I, lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+    const int i0 = cam_item_ptr[I.cam], i1 = cam_item_ptr[I.cam + 1];
+    if (i1 - i0 == 1) {
+      if (lane < 9) y[9 * (size_t)I.cam + lane] = partial[9 * (size_t)it + lane];
+      continue;
+    }
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(cam_cnt + I.cam, 1) == i1 - i0 - 1) ? 1 : 0;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      if (lane < 9) {
+        S sacc = 0;
+        for (int q = i0; q < i1; ++q) sacc += __ldcg(partial + 9 * (size_t)q + lane);
+        y[9 * (size_t)I.cam + lane] = sacc;
+      }
+      if (lane == 0) cam_cnt[I.cam] = 0;
+    }
+  }
 }
 
 // out[cam*9+c] = sum over the camera's items (fixed order)
@@ -1304,8 +1356,7 @@ __device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const Matve
 template <class S, int WARPS, int NS, int STAGE_BYTES>
 __global__ void __launch_bounds__(WARPS * 32) k_matvec_small_tma(DevPtrs<S> D, const MatvecItem* __restrict__ items,
                                                                   int item_begin, int item_end, int scratch_per_warp,
-                                                                  const S* __restrict__ xvec, const int* done) {
-  if (done && *done) return;
+                                                                  const S* __restrict__ xvec, const int* done, int pdl) {
   extern __shared__ __align__(128) unsigned char smem_tma[];
   __shared__ __align__(8) uint64_t bars_all[WARPS][NS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1322,9 +1373,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_matvec_small_tma(DevPtrs<S> D, c
   PanelStream<S> ps;
   ps.src = nullptr; ps.rows_left = 0; ps.row_scalars = 0; ps.rows_per_stage = 1; ps.next_item = first; ps.issued = 0; ps.policy = l2_evict_first_policy();
   unsigned consumed = 0;
+  // the panel stream does not depend on the previous kernel (the panels are constant during PCG): prime the ring first,
+  // then wait for the grid dependency (programmatic dependent launch), then read x / the done flag
 #pragma unroll 1
   for (int s = 0; s < NS; ++s)
     if (!stream_produce<S, NS, STAGE_BYTES>(ps, D, items, item_end, stride, ring, bars, lane)) break;
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (done && *done) {
+    // drain the bulk copies already in flight before the CTA may exit
+    for (unsigned s = 0; s < ps.issued; ++s) mbar_wait(&bars[s % NS], (s / NS) & 1u);
+    return;
+  }
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int q = first; q < item_end; q += stride) {
     const MatvecItem it = items[q];
     const TileInfo T = D.tiles[it.tile];
@@ -1431,14 +1491,18 @@ __global__ void k_cam_final9(const S* __restrict__ partial, const int* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// PCG vector step on ONE thread-block cluster (hardware cluster barriers, ~0.2 us, instead of kernel boundaries):
+// PCG vector step on ONE thread-block cluster (hardware cluster barriers instead of kernel boundaries):
 //   P1  q = y + lambda * v, partial v.q                       (v = p, or x in the residual-refresh half step)
 //   P2  alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = M^-1 r ; partial r.z and x.(b + r)
 //   P3  Nash-Sofer test zeta = i (Q_i - Q_{i-1}) / Q_i < eta ; rho, beta ; p = z + beta p   (next iteration's p)
 // ref: cg/conjugate_gradient.hpp:161-295 ; scalars in double, vectors in Scalar, alpha/beta narrowed to Scalar.
 // mode 0 regular iteration, 1 refresh first half (stop after x += alpha p), 2 refresh second half (v = x,
 // r = b - H x), 3 initialisation (x = 0, r = b, z, rho, p = z).  part: [gridDim][4] doubles.
-// yfull != 0: y was already reduced over cameras (and shards) into D.y; else y = sum of the camera's item partials.
+// y = D.y holds the camera-reduced (and, with several shards, all-reduced) operator output.
+// Cameras are dealt to the CTAs in contiguous ranges; thread t of a CTA owns elements e0 + t + k * blockDim.  Everything
+// that does not depend on the operator output (x, r, p, b and the 9-float row of M^-1) is fetched before the grid
+// dependency is awaited and stays in registers across the phases (EPT elements per thread); the new residual of a
+// camera is exchanged through shared memory.  Larger problems loop over rounds and re-read from global memory.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cluster_sync_all() {
   __threadfence();
@@ -1446,36 +1510,65 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+constexpr int VEC_THREADS = 512;
+constexpr int VEC_EPT = 2;
+
 template <class S>
-__global__ void __launch_bounds__(512) k_pcg_vec(DevPtrs<S> D, PcgState* st, const int* __restrict__ cam_item_ptr,
-                                                 double* part, S lambda, int i, int mode, int yfull, double eta, int min_it,
-                                                 int is_last) {
-  if (st->done) return;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
-  const int n9 = 9 * D.nc;
+__global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState* st, double* part, S lambda, int i, int mode,
+                                                         double eta, int min_it, int is_last, int pdl) {
+  __shared__ S sr[VEC_THREADS * VEC_EPT + 16];
+  const int tid = threadIdx.x;
+  const int cams_per_block = (D.nc + gridDim.x - 1) / gridDim.x;
+  const int cam0 = min(D.nc, (int)blockIdx.x * cams_per_block);
+  const int cam1 = min(D.nc, cam0 + cams_per_block);
+  const int e0 = 9 * cam0, ne = 9 * (cam1 - cam0);
+  const bool cached = ne <= VEC_THREADS * VEC_EPT;
   const int cur = i & 1, nxt = cur ^ 1;
+  // ---- prefetch of everything that does not depend on the previous kernel of this iteration ----
+  S xv[VEC_EPT], rv[VEC_EPT], pv[VEC_EPT], bv[VEC_EPT], qv[VEC_EPT], zv[VEC_EPT], inv[VEC_EPT][9];
+  if (cached) {
+#pragma unroll
+    for (int k = 0; k < VEC_EPT; ++k) {
+      const int l = tid + k * VEC_THREADS;
+      const bool on = l < ne;
+      const int e = e0 + (on ? l : 0);
+      xv[k] = on ? D.x[e] : S(0); rv[k] = on ? D.r[e] : S(0); pv[k] = on ? D.p[e] : S(0); bv[k] = on ? D.b[e] : S(0);
+      const S* row = D.inv + 9 * (size_t)e;  // inv[cam][a][:] = 9 consecutive scalars at 81 cam + 9 a = 9 e
+#pragma unroll
+      for (int c = 0; c < 9; ++c) inv[k][c] = on ? row[c] : S(0);
+      qv[k] = 0; zv[k] = 0;
+    }
+  }
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (st->done) return;
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  double alpha = 0;
   if (mode != 3) {
     // ---- P1 ----
-    const S* vec = (mode == 2) ? D.x : D.p;
     double acc = 0;
-    for (int e = tid; e < n9; e += nthr) {
-      S yv;
-      if (yfull) yv = D.y[e];
-      else {
-        const int cam = e / 9, c = e - 9 * cam;
-        yv = 0;
-        for (int it = cam_item_ptr[cam]; it < cam_item_ptr[cam + 1]; ++it) yv += D.partial[9 * (size_t)it + c];
+    if (cached) {
+#pragma unroll
+      for (int k = 0; k < VEC_EPT; ++k) {
+        const int l = tid + k * VEC_THREADS;
+        if (l < ne) {
+          const S vv = (mode == 2) ? xv[k] : pv[k];
+          qv[k] = __ldcg(D.y + e0 + l) + lambda * vv;
+          acc += (double)(vv * qv[k]);
+        }
       }
-      const S pv = vec[e];
-      const S qv = yv + lambda * pv;
-      D.q[e] = qv;
-      acc += (double)(pv * qv);
+    } else {
+      const S* vec = (mode == 2) ? D.x : D.p;
+      for (int l = tid; l < ne; l += VEC_THREADS) {
+        const S vv = vec[e0 + l];
+        const S q = __ldcg(D.y + e0 + l) + lambda * vv;
+        D.q[e0 + l] = q;
+        acc += (double)(vv * q);
+      }
     }
     if (mode != 2) block_sum_store4(acc, part, 0);
     cluster_sync_all();
   }
   // ---- P2 ----
-  double alpha = 0;
   if (mode == 0 || mode == 1) {
     const double pq = block_sum_partials(part, gridDim.x, 4, 0);
     bool fail = false;
@@ -1486,58 +1579,81 @@ __global__ void __launch_bounds__(512) k_pcg_vec(DevPtrs<S> D, PcgState* st, con
       if (isinf(alpha)) { fail = true; term = 2; reason = 6; }
     }
     if (fail) {  // uniform across the cluster: nobody reaches the next barrier
-      for (int e = tid; e < n9; e += nthr) D.inc[e] = -D.x[e];
-      if (tid == 0) { st->done = 1; st->term = term; st->reason = reason; st->last_pq = pq; st->iter = i; }
+      for (int l = tid; l < ne; l += VEC_THREADS) D.inc[e0 + l] = -D.x[e0 + l];
+      if (blockIdx.x == 0 && tid == 0) { st->done = 1; st->term = term; st->reason = reason; st->last_pq = pq; st->iter = i; }
       return;
     }
-    if (tid == 0) { st->last_pq = pq; st->last_alpha = alpha; }
+    if (blockIdx.x == 0 && tid == 0) { st->last_pq = pq; st->last_alpha = alpha; }
   }
   const S as = (S)alpha;
   if (mode == 1) {
-    for (int e = tid; e < n9; e += nthr) D.x[e] = D.x[e] + as * D.p[e];
+    if (cached) {
+#pragma unroll
+      for (int k = 0; k < VEC_EPT; ++k) { const int l = tid + k * VEC_THREADS; if (l < ne) D.x[e0 + l] = xv[k] + as * pv[k]; }
+    } else {
+      for (int l = tid; l < ne; l += VEC_THREADS) D.x[e0 + l] = D.x[e0 + l] + as * D.p[e0 + l];
+    }
     return;
   }
-  {
-    // cameras are dealt to the CTAs in contiguous ranges; inside a CTA thread (cam, a) owns element 9 cam + a, so the
-    // residual of a whole camera is produced and consumed by the same CTA (a __syncthreads() orders P2a -> P2b).
-    const int cams_per_block = (D.nc + gridDim.x - 1) / gridDim.x;
-    const int cam0 = blockIdx.x * cams_per_block;
-    const int cam1 = min(D.nc, cam0 + cams_per_block);
-    const int e0 = 9 * cam0, e1 = 9 * cam1;
-    // P2a: x and r (elementwise)
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-      S rv;
-      if (mode == 0) {
-        D.x[e] = D.x[e] + as * D.p[e];
-        rv = D.r[e] - as * D.q[e];
-      } else if (mode == 2) {
-        rv = D.b[e] - D.q[e];
-      } else {
-        D.x[e] = 0;
-        rv = D.b[e];
+  double rz = 0, xbr = 0, bb = 0;
+  if (cached) {
+    // P2a: x and r in registers, new residual to shared memory
+#pragma unroll
+    for (int k = 0; k < VEC_EPT; ++k) {
+      const int l = tid + k * VEC_THREADS;
+      if (l < ne) {
+        if (mode == 0) { xv[k] = xv[k] + as * pv[k]; rv[k] = rv[k] - as * qv[k]; }
+        else if (mode == 2) { rv[k] = bv[k] - qv[k]; }
+        else { xv[k] = 0; rv[k] = bv[k]; }
+        sr[l] = rv[k];
       }
-      D.r[e] = rv;
     }
     __syncthreads();
-    // P2b: z = M^-1 r (9x9 block row per thread, ref: cg/preconditioner.hpp:122-136) and the dot products
-    double rz = 0, xbr = 0, bb = 0;
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-      const int cam = e / 9, a = e - 9 * cam;
-      const S* row = D.inv + 81 * (size_t)cam + 9 * a;
-      const S* rc = D.r + 9 * (size_t)cam;
-      S zv = 0;
+    // P2b: z = M^-1 r (ref: cg/preconditioner.hpp:122-136) and the dot products
 #pragma unroll
-      for (int b2 = 0; b2 < 9; ++b2) zv += row[b2] * rc[b2];
-      D.z[e] = zv;
-      const S rv = rc[a];
-      rz += (double)(rv * zv);
-      xbr += (double)(D.x[e] * (D.b[e] + rv));
-      bb += (double)(rv * rv);
+    for (int k = 0; k < VEC_EPT; ++k) {
+      const int l = tid + k * VEC_THREADS;
+      if (l < ne) {
+        const S* rc = sr + 9 * (l / 9);
+        S z = 0;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) z += inv[k][c] * rc[c];
+        zv[k] = z;
+        rz += (double)(rv[k] * z);
+        xbr += (double)(xv[k] * (bv[k] + rv[k]));
+        bb += (double)(rv[k] * rv[k]);
+        D.x[e0 + l] = xv[k];
+        D.r[e0 + l] = rv[k];
+      }
     }
-    block_sum_store4(rz, part, 1);
-    block_sum_store4(xbr, part, 2);
-    block_sum_store4(bb, part, 3);
+  } else {
+    for (int l = tid; l < ne; l += VEC_THREADS) {
+      const int e = e0 + l;
+      S r2;
+      if (mode == 0) { D.x[e] = D.x[e] + as * D.p[e]; r2 = D.r[e] - as * D.q[e]; }
+      else if (mode == 2) { r2 = D.b[e] - D.q[e]; }
+      else { D.x[e] = 0; r2 = D.b[e]; }
+      D.r[e] = r2;
+    }
+    __syncthreads();
+    for (int l = tid; l < ne; l += VEC_THREADS) {
+      const int e = e0 + l;
+      const int cam = e / 9;
+      const S* row = D.inv + 9 * (size_t)e;
+      const S* rc = D.r + 9 * (size_t)cam;
+      S z = 0;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) z += row[c] * rc[c];
+      D.z[e] = z;
+      const S r2 = D.r[e];
+      rz += (double)(r2 * z);
+      xbr += (double)(D.x[e] * (D.b[e] + r2));
+      bb += (double)(r2 * r2);
+    }
   }
+  block_sum_store4(rz, part, 1);
+  block_sum_store4(xbr, part, 2);
+  block_sum_store4(bb, part, 3);
   cluster_sync_all();
   // ---- P3 ----
   const double rho_new = block_sum_partials(part, gridDim.x, 4, 1);
@@ -1547,8 +1663,8 @@ __global__ void __launch_bounds__(512) k_pcg_vec(DevPtrs<S> D, PcgState* st, con
     norm_b = sqrt(block_sum_partials(part, gridDim.x, 4, 3));
     if (norm_b == 0.0) { done = 1; term = 1; reason = 2; }
   } else {
-    const double xbr = block_sum_partials(part, gridDim.x, 4, 2);
-    q1 = -xbr;
+    const double xbr_t = block_sum_partials(part, gridDim.x, 4, 2);
+    q1 = -xbr_t;
     zeta = (double)i * (q1 - st->q0[cur]) / q1;
     if (zeta < eta && i >= min_it) { done = 1; term = 1; reason = 1; }
   }
@@ -1559,14 +1675,24 @@ __global__ void __launch_bounds__(512) k_pcg_vec(DevPtrs<S> D, PcgState* st, con
       if (beta == 0.0 || isinf(beta)) { done = 1; term = 2; reason = 4; }
     }
   }
-  if (!done && !is_last) {
-    const S bs = (S)beta;
-    for (int e = tid; e < n9; e += nthr) D.p[e] = (mode == 3) ? D.z[e] : D.z[e] + bs * D.p[e];
+  const S bs = (S)beta;
+  if (cached) {
+#pragma unroll
+    for (int k = 0; k < VEC_EPT; ++k) {
+      const int l = tid + k * VEC_THREADS;
+      if (l < ne) {
+        if (!done && !is_last) D.p[e0 + l] = (mode == 3) ? zv[k] : zv[k] + bs * pv[k];
+        if (done || is_last) D.inc[e0 + l] = -xv[k];
+      }
+    }
+  } else {
+    for (int l = tid; l < ne; l += VEC_THREADS) {
+      const int e = e0 + l;
+      if (!done && !is_last) D.p[e] = (mode == 3) ? D.z[e] : D.z[e] + bs * D.p[e];
+      if (done || is_last) D.inc[e] = -D.x[e];
+    }
   }
-  if (done || is_last) {
-    for (int e = tid; e < n9; e += nthr) D.inc[e] = -D.x[e];
-  }
-  if (tid == 0) {
+  if (blockIdx.x == 0 && tid == 0) {
     st->rho[nxt] = rho_new;  // iteration i+1 reads slot (i+1)&1
     st->q0[nxt] = (mode == 3) ? 0.0 : q1;
     st->last_zeta = zeta;

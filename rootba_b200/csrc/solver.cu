@@ -89,6 +89,8 @@ struct Solver : rba_handle {
   double* d_part_pq = nullptr;   // [NPART]
   double* d_part4 = nullptr;     // [grid][4] partials of the fused PCG step
   int pcg_cluster = 16;
+  bool use_pdl = true;
+  int* d_cam_cnt = nullptr;      // per-camera arrival counters of k_cam_reduce_final (zero between launches)
   double* d_epart = nullptr;     // [EBLOCKS][6]
   double* d_red = nullptr;       // [8] reduced doubles (error / l_diff)
   int* d_flags = nullptr;        // [4] bad flags
@@ -231,7 +233,7 @@ struct Solver : rba_handle {
     TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
     TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
     TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
-    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4));
+    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4)); TRY(dalloc(&d_cam_cnt, (size_t)nc));
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_state, 1));
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
@@ -274,10 +276,11 @@ struct Solver : rba_handle {
       // the PCG vector step runs on one thread-block cluster (16 CTAs if the device grants it, else 8)
       CU(cudaFuncSetAttribute(k_pcg_vec<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       pcg_cluster = 16;
+      if (const char* e = getenv("RBA_PDL")) use_pdl = atoi(e) != 0;
       if (const char* e = getenv("RBA_PCG_CLUSTER")) pcg_cluster = std::max(1, std::min(atoi(e), 16));
       for (; pcg_cluster > 1; pcg_cluster >>= 1) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(pcg_cluster); cfg.blockDim = dim3(512);
+        cfg.gridDim = dim3(pcg_cluster); cfg.blockDim = dim3(VEC_THREADS);
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = pcg_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -366,6 +369,21 @@ struct Solver : rba_handle {
     return RBA_OK;
   }
 
+  // launch with optional programmatic dependent launch (the kernel may start before its predecessor in the stream has
+  // finished and orders itself with griddepcontrol.wait) and optional thread-block-cluster dimension
+  template <class... KArgs, class... Args>
+  int launch_ex(void (*kern)(KArgs...), int grid, int block, size_t smem, bool pdl, int cluster, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    if (cluster > 1) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; ++na; }
+    cfg.attrs = at; cfg.numAttrs = na;
+    CU(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+    ++launches;
+    return RBA_OK;
+  }
   int tile_grid(int max_blocks) const { return std::max(1, std::min(max_blocks, (D.ntiles + TILE_WARPS - 1) / TILE_WARPS)); }
   int grid_for(long long work_items, int per_block, int blocks_per_sm) const {
     long long g = (work_items + per_block - 1) / per_block;
@@ -448,7 +466,7 @@ struct Solver : rba_handle {
     k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, done);
     ++launches;
   }
-  void matvec_kernels(const S* xvec, const int* done) {
+  void matvec_kernels(const S* xvec, const int* done, bool pdl = false) {
     const int nitems = (int)L.items.size();
     if (L.n_items_large > 0) {
       k_matvec_large<S, K4_WARPS, KPMAX><<<grid_for(L.n_items_large, K4_WARPS, 4), K4_WARPS * 32, k4_smem_small, stream>>>(
@@ -456,37 +474,30 @@ struct Solver : rba_handle {
       ++launches;
     }
     if (nitems > L.n_items_large) {
-      if (use_tma)
-        k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE><<<grid_for(nitems - L.n_items_large, K4_WARPS, k4_tma_blocks_per_sm), K4_WARPS * 32, k4_smem_tma, stream>>>(
-            D, d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done);
-      else
+      if (use_tma) {
+        launch_ex(k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>, grid_for(nitems - L.n_items_large, K4_WARPS, k4_tma_blocks_per_sm), K4_WARPS * 32,
+                  k4_smem_tma, pdl && use_pdl && L.n_items_large == 0, 1, D, (const MatvecItem*)d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done,
+                  (int)(pdl && use_pdl && L.n_items_large == 0));
+        --launches;
+      } else
         k_matvec_small<S, K4_WARPS><<<grid_for(nitems - L.n_items_large, K4_WARPS, 5), K4_WARPS * 32, k4_smem_small, stream>>>(
             D, d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done);
       ++launches;
     }
     ++tm.matvec_launches;
   }
-  int pcg_vec(int i, int mode, int yfull, int is_last, S lambda) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(pcg_cluster); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = pcg_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, k_pcg_vec<S>, D, d_state, (const int*)d_csr_y_item_ptr, d_part4, lambda, i, mode, yfull,
-                          (double)opt.eta, (int)opt.min_linear_solver_iterations, is_last));
-    ++launches;
-    return RBA_OK;
+  int pcg_vec(int i, int mode, bool pdl, int is_last, S lambda) {
+    return launch_ex(k_pcg_vec<S>, pcg_cluster, VEC_THREADS, 0, pdl && use_pdl, pcg_cluster, D, d_state, d_part4, lambda, i, mode, (double)opt.eta,
+                     (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl));
   }
   // finish one operator application inside PCG (H v for v = p in mode 0/1, x in mode 2) and do the vector step
   int pcg_apply(int i, int mode, int is_last, S lambda) {
-    k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, &d_state->done);
-    ++launches;
-    if (opt.nranks == 1) return pcg_vec(i, mode, 0, is_last, lambda);
-    k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, d_csr_y_item_ptr, nc, D.y, &d_state->done);
-    ++launches;
-    int rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
-    return pcg_vec(i, mode, 1, is_last, lambda);
+    int rc = launch_ex(k_cam_reduce_final<S>, grid_for(n_y_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, (const int*)d_csr_y_slots,
+                       (const ReduceItem*)d_csr_y_items, n_y_items, (const int*)d_csr_y_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl);
+    if (rc) return rc;
+    if (opt.nranks == 1) return pcg_vec(i, mode, true, is_last, lambda);
+    rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
+    return pcg_vec(i, mode, false, is_last, lambda);
   }
   // q_out = H vec = sum + lambda vec ; optional partial p.q
   int matvec_finish(const S* vec, S* out, S lambda, PcgState* st, double* part) {
@@ -529,7 +540,7 @@ struct Solver : rba_handle {
     const int max_it = std::max(opt.max_linear_solver_iterations, 1);
     const int period = opt.residual_reset_period;
     const int chk = opt.pcg_check_period;
-    rc = pcg_vec(0, 3, 0, 0, lambda); if (rc) return rc;  // x = 0, r = b, z = M^-1 r, rho, p = z
+    rc = pcg_vec(0, 3, false, 0, lambda); if (rc) return rc;  // x = 0, r = b, z = M^-1 r, rho, p = z
     int i = 1;
     int pending[2] = {0, 0};
     int slot = 0;
@@ -538,10 +549,10 @@ struct Solver : rba_handle {
       const int chunk_end = std::min(i + chk - 1, max_it);
       for (; i <= chunk_end; ++i) {
         const int is_last = (i == max_it) ? 1 : 0;
-        matvec_kernels(D.p, &d_state->done);
+        matvec_kernels(D.p, &d_state->done, true);
         if (i % period == 0) {
           rc = pcg_apply(i, 1, 0, lambda); if (rc) return rc;
-          matvec_kernels(D.x, &d_state->done);
+          matvec_kernels(D.x, &d_state->done, true);
           rc = pcg_apply(i, 2, is_last, lambda); if (rc) return rc;
         } else {
           rc = pcg_apply(i, 0, is_last, lambda); if (rc) return rc;
