@@ -12,7 +12,7 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librootba_b200.so")
+LIB_PATH = os.environ.get("RBA_LIB", os.path.join(_HERE, "librootba_b200.so"))
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rootba_b200.h")
 
 RBA_OK = 0

@@ -1353,8 +1353,11 @@ __device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const Matve
 // K4 (TMA variant): persistent warps, each streams the panels of its items through a private NS-stage
 // shared-memory ring (cp.async.bulk + mbarrier complete_tx), so the bytes in flight per SM are set by the
 // ring size (WARPS * NS * STAGE_BYTES) instead of by registers.
+#ifndef RBA_K4_MINB
+#define RBA_K4_MINB 1
+#endif
 template <class S, int WARPS, int NS, int STAGE_BYTES>
-__global__ void __launch_bounds__(WARPS * 32) k_matvec_small_tma(DevPtrs<S> D, const MatvecItem* __restrict__ items,
+__global__ void __launch_bounds__(WARPS * 32, RBA_K4_MINB) k_matvec_small_tma(DevPtrs<S> D, const MatvecItem* __restrict__ items,
                                                                   int item_begin, int item_end, int scratch_per_warp,
                                                                   const S* __restrict__ xvec, const int* done, int pdl) {
   extern __shared__ __align__(128) unsigned char smem_tma[];

@@ -306,8 +306,14 @@ struct Solver : rba_handle {
     return RBA_OK;
   }
   static constexpr int K4_WARPS = 4;
-  static constexpr int K4_NS = 3;             // TMA ring stages per warp
-  static constexpr int K4_STAGE = 4608;       // bytes per stage (2 rows of an f32 KP=9 tile)
+#ifndef RBA_K4_NS
+#define RBA_K4_NS 2
+#endif
+#ifndef RBA_K4_STAGE
+#define RBA_K4_STAGE 4608
+#endif
+  static constexpr int K4_NS = RBA_K4_NS;        // TMA ring stages per warp
+  static constexpr int K4_STAGE = RBA_K4_STAGE;  // bytes per stage (2 rows of an f32 KP=9 tile)
   static constexpr int TILE_WARPS = 4;
   static constexpr int K1_CAP = 3904;   // scalars of shared memory per warp: linearize+QR needs 60 * W * n + 64 (= 3904 for the standard tiles)
   static constexpr int K2_CAP = 2944;   // stage 2 needs 3 * W * CS + 9 * W * n + 16 W + 8 (<= 2944 for the standard tiles)
