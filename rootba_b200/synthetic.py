@@ -10,7 +10,10 @@ spec in SURVEY.md section 8(d):
   track length n = 2 + Geometric(p = 1/(mean_n - 1)) truncated at min(Nc, 400);
   cameras per landmark uniform without replacement, sorted ascending (the
   std::map order of the reference, bal/bal_problem.hpp:137);
-  observation = projection + N(0, 0.5^2) px; only z > 0.1 kept.
+  observation = projection + N(0, 0.5^2) px; only z > 0.1 kept -- and, beyond that spec, only observations inside a
+  +-45 degree field of view (|x/z|, |y/z| <= 1): without it a dense camera ring produces grazing observations with
+  x/z ~ 1e2 whose r^4 distortion term dominates the whole cost (1e20 for the Final-13682 shape), which no real BAL
+  file contains.
 
 Internal conventions are the reference's *after loading* (bal/bal_problem.cpp:189-282):
 camera looks along +z, image y points down, no minus sign in the projection;
@@ -104,15 +107,19 @@ def so3_exp(w: np.ndarray) -> np.ndarray:
     return np.concatenate([k * w, np.cos(half)], axis=-1)
 
 
-def project(cams: np.ndarray, p_w: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+def project(cams: np.ndarray, p_w: np.ndarray, return_tan: bool = False):
     """Snavely projection in the loaded convention.  cams [m, 10], p_w [m, 3] -> (xy [m, 2], z [m])."""
     R = quat_to_rot(cams[:, :4])
     pc = np.einsum("mij,mj->mi", R, p_w) + cams[:, 4:7]
     z = pc[:, 2]
-    m = pc[:, :2] / z[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m = pc[:, :2] / z[:, None]
     r2 = (m * m).sum(axis=1)
     rp = 1.0 + cams[:, 8] * r2 + cams[:, 9] * r2 * r2
-    return cams[:, 7:8] * rp[:, None] * m, z
+    xy = cams[:, 7:8] * rp[:, None] * m
+    if return_tan:
+        return xy, z, np.abs(m).max(axis=1)
+    return xy, z
 
 
 def _sample_tracks(rng: np.random.Generator, nc: int, n: np.ndarray) -> np.ndarray:
@@ -142,7 +149,7 @@ def _sample_tracks(rng: np.random.Generator, nc: int, n: np.ndarray) -> np.ndarr
     return out
 
 
-def synth_bal(nc: int, nl: int, mean_n: float, seed: int = 38401, *, max_track: int = 400,
+def synth_bal(nc: int, nl: int, mean_n: float, seed: int = 38401, *, max_track: int = 400, max_tan: float = 1.0,
               obs_noise: float = 0.5, perturb_lm: float = 0.05, perturb_rot: float = 0.002,
               perturb_trans: float = 0.01, normalize_scale: float | None = 100.0) -> BalArrays:
     """Generate a synthetic BAL problem (already in the loaded convention), optionally normalised
@@ -174,9 +181,9 @@ def synth_bal(nc: int, nl: int, mean_n: float, seed: int = 38401, *, max_track: 
     n = np.minimum(n, min(nc, max_track)).astype(np.int64)
     obs_cam = _sample_tracks(rng, nc, n)
     lm_of_obs = np.repeat(np.arange(nl), n)
-    xy, z = project(cams[obs_cam], lms[lm_of_obs])
+    xy, z, tan = project(cams[obs_cam], lms[lm_of_obs], return_tan=True)
     xy = xy + rng.normal(0, obs_noise, xy.shape)
-    keep = z > 0.1
+    keep = (z > 0.1) & (tan <= max_tan)
     # drop bad observations, then landmarks with < 2 observations (QR needs n >= 2, ipp:73-76)
     n_keep = np.bincount(lm_of_obs[keep], minlength=nl)
     lm_ok = n_keep >= 2

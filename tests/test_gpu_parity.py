@@ -1,7 +1,7 @@
 """GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs.
 
 Tolerances (relative norm ||a-b||/(||a||+||b||), reference testing/eigen_utils.hpp:104-108):
-  single stage, identical inputs:   f32 5e-5 (1e-5 on the reference's fixture; see test_oracle_properties.py), f64 1e-11
+  single stage, identical inputs:   f32 1e-5 (the reference's default_test_precision, testing/float_utils.hpp:62-69), f64 1e-11
   after a PCG solve (inc, l_diff):  f32 2e-3, f64 1e-8   (error growth through PCG; CG iteration count +-2)
   indices / counts:                 bit-exact
 """
@@ -12,7 +12,7 @@ from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 
-TOL1 = {np.float32: 5e-5, np.float64: 1e-11}
+TOL1 = {np.float32: 1e-5, np.float64: 1e-11}
 TOLS = {np.float32: 2e-3, np.float64: 1e-8}
 
 
@@ -163,7 +163,10 @@ def test_lm_trajectory(small_problem, dtype, kw):
     summ = rb.bundle_adjust_manual(bp, so, linearizor=lin)
     rows, term = o.optimize()
     g_it = summ["iterations"]
-    assert len(g_it) == len(rows)
+    if dtype == np.float64:
+        assert len(g_it) == len(rows)
+    else:  # f32: the function-tolerance stop (|dcost| <= 1e-6 cost) is decided by round-off at convergence
+        assert abs(len(g_it) - len(rows)) <= 1
     # f32: the initial synthetic cost is dominated by a few near-camera outliers and carries ~1e-4 of round-off
     # (oracle-f32 vs oracle-f64, see test_compute_error); f64 pins the trajectory at 1e-9.
     # f32 trajectories drift apart by a few 1e-3 after several LM iterations (different but equally valid f32
@@ -187,6 +190,7 @@ def test_lm_trajectory(small_problem, dtype, kw):
                 assert abs(a["linear_solver_iterations"] - int(b["cg_iterations"])) <= slack, a["iteration"]
         prev = b["cost"]
     assert g_it[-1]["cost"]["all"]["error"] < 0.2 * g_it[0]["cost"]["all"]["error"]
+    assert abs(g_it[-1]["cost"]["all"]["error"] - rows[-1]["cost"]) <= max(tol, 1e-6) * rows[-1]["cost"]
     lin.close()
 
 

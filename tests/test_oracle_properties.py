@@ -13,11 +13,8 @@ from conftest import rel_err
 from oracle import oracle_py as orc
 from rootba_b200 import synthetic as syn
 
-# testing/float_utils.hpp:62-69 gives 1e-5 (f32) / 1e-12 (f64) on the reference's real fixture.  On the
-# synthetic stand-in (perturbed state => larger residuals and more cancellation in b) float32 round-off
-# of two algebraically different formulations reaches ~1.5e-5, so f32 uses 5e-5; f64 keeps 1e-12,
-# which is what pins the algebra.
-PREC = {np.float32: 5e-5, np.float64: 1e-12}
+# testing/float_utils.hpp:62-69: default_test_precision = 1e-5 (f32) / 1e-12 (f64), the reference's own bar
+PREC = {np.float32: 1e-5, np.float64: 1e-12}
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -114,7 +111,7 @@ def test_qr_sc_equivalence(small_problem, dtype, use_householder):
         assert ok
         scaling = (1.0 / (eps + np.sqrt(d2.astype(np.float64)))).astype(dtype)
         d2_sc = sc.sc_linearize()
-        assert rel_err(d2, d2_sc) < 2 * prec * (10 if dtype == np.float32 else 1)  # solver/bal_bundle_adjustment.test.cpp:60,83-86 (f32: summation-order noise)
+        assert rel_err(d2, d2_sc) < 2 * prec  # solver/bal_bundle_adjustment.test.cpp:60,83-86
         qr.set_pose_damping(pose_damping)
         b_qr, blocks_qr = qr.stage2(lam, scaling, schur_blocks=True)
         sc.sc_scale_Jp(scaling)
