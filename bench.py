@@ -206,6 +206,20 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def host_threads() -> int:
+    """threads for the CPU arm: one per physical core (the landmark loop is memory-bound; SMT siblings only add contention)"""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        n = os.cpu_count()
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, int(n))
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -246,8 +260,8 @@ def bench_reference(args):
     from oracle import oracle_py as orc
     dtype = np.float32 if args.dtype == "f32" else np.float64
     arrays = make_problem(args)
-    cores = orc.max_threads()
-    o = orc.Oracle(arrays, dtype, orc.default_options(num_threads=0))
+    cores = host_threads()
+    o = orc.Oracle(arrays, dtype, orc.default_options(num_threads=cores))
     secs, wall, st = run_lm(OracleBackend(o), dtype, args.warmup, args.steps)
     ms = 1e3 * secs / args.steps
     st_ = arrays.stats()
@@ -303,10 +317,10 @@ def bench_ours(args):
             torch.cuda.synchronize()
 
     # ---- device-resident run (value) ----
-    lin = make_linearizor()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    lin = make_linearizor()
     l0 = lin.timings()["kernel_launches"]
     # warm-up outside, then K timed steps bracketed by barrier + synchronize, CUDA events on the solver stream
     st = LMStepper(GpuBackend(lin), dtype)
@@ -330,14 +344,14 @@ def bench_ours(args):
     wall_s = time.perf_counter() - t0
     barrier()
     launches = lin.timings()["kernel_launches"] - l0
-    clocks = sampler.stop() if rank == 0 else {}
     secs = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(secs, op=dist.ReduceOp.MAX)
     ms = 1e3 * float(secs.item()) / args.steps
     # ---- roofline of the dominant kernel (rcs_matvec), timed alone with CUDA events ----
-    mv_s = lin.time_matvec(30)
+    mv_s = lin.time_matvec(200)
     stats = lin.stats()
+    clocks = sampler.stop() if rank == 0 else {}
     mv_t = torch.tensor([mv_s], dtype=torch.float64, device="cuda")
     mv_bytes = torch.tensor([float(stats["matvec_algorithmic_bytes"])], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -372,10 +386,10 @@ def bench_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle_py as orc
-        o = orc.Oracle(arrays, dtype, orc.default_options(num_threads=0))
+        o = orc.Oracle(arrays, dtype, orc.default_options(num_threads=host_threads()))
         n_cpu = min(args.steps, 2)
         cs, _, stc = run_lm(OracleBackend(o), dtype, args.warmup, n_cpu)
-        cpu = {"value": 1e3 * cs / n_cpu, "unit": "ms/LM-iter", "cores": orc.max_threads(), "kind": "port",
+        cpu = {"value": 1e3 * cs / n_cpu, "unit": "ms/LM-iter", "cores": host_threads(), "kind": "port",
                "sample": f"LM iterations {args.warmup + 1}..{args.warmup + n_cpu} of the same trajectory on the host cores "
                          f"(CPU restatement of the reference, OpenMP over landmarks; warm-up iterations untimed)",
                "cg_iterations": [r.get("cg_iterations") for r in stc.log[args.warmup:]]}

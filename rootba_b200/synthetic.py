@@ -9,7 +9,10 @@ spec in SURVEY.md section 8(d):
   f ~ U(500, 2000), k1 ~ N(0, 1e-7), k2 ~ N(0, 1e-13); landmarks ~ N(0, 3^2 I);
   track length n = 2 + Geometric(p = 1/(mean_n - 1)) truncated at min(Nc, 400);
   cameras per landmark uniform without replacement, sorted ascending (the
-  std::map order of the reference, bal/bal_problem.hpp:137);
+  std::map order of the reference, bal/bal_problem.hpp:137) -- `locality > 0` (used by the BASELINE-config stand-ins,
+  synth_config) instead draws them from a window of `locality * n` consecutive camera indices, i.e. sequence-like
+  visibility: uniformly random visibility is an expander graph whose reduced camera system is so well conditioned that
+  PCG stops after 2-5 iterations, unlike any real BAL problem;
   observation = projection + N(0, 0.5^2) px; only z > 0.1 kept -- and, beyond that spec, only observations inside a
   +-45 degree field of view (|x/z|, |y/z| <= 1): without it a dense camera ring produces grazing observations with
   x/z ~ 1e2 whose r^4 distortion term dominates the whole cost (1e20 for the Final-13682 shape), which no real BAL
@@ -122,6 +125,26 @@ def project(cams: np.ndarray, p_w: np.ndarray, return_tan: bool = False):
     return xy, z
 
 
+def _sample_tracks_local(rng: np.random.Generator, nc: int, n: np.ndarray, window_factor: float) -> np.ndarray:
+    """Sequence-like visibility (what a vehicle-mounted Ladybug rig produces): landmark l is seen by n[l] distinct cameras
+    drawn from a window of ~window_factor * n[l] consecutive camera indices around a random centre (wrapping)."""
+    total = int(n.sum())
+    off = np.concatenate([[0], np.cumsum(n)])
+    out = np.empty(total, dtype=np.int32)
+    for k in np.unique(n):
+        idx = np.nonzero(n == k)[0]
+        m = idx.size
+        w = int(min(nc, max(k, round(window_factor * k))))
+        centre = rng.integers(0, nc, size=m)
+        keys = rng.random((m, w))
+        rel = np.argsort(keys, axis=1)[:, :k]                      # k distinct offsets inside the window
+        sel = ((centre[:, None] + rel - w // 2) % nc).astype(np.int32)
+        sel.sort(axis=1)
+        pos = (off[idx][:, None] + np.arange(k)[None, :]).ravel()
+        out[pos] = sel.ravel()
+    return out
+
+
 def _sample_tracks(rng: np.random.Generator, nc: int, n: np.ndarray) -> np.ndarray:
     """For each landmark l sample n[l] distinct cameras in [0, nc), sorted ascending; flat array."""
     total = int(n.sum())
@@ -150,6 +173,7 @@ def _sample_tracks(rng: np.random.Generator, nc: int, n: np.ndarray) -> np.ndarr
 
 
 def synth_bal(nc: int, nl: int, mean_n: float, seed: int = 38401, *, max_track: int = 400, max_tan: float = 1.0,
+              locality: float = 0.0,
               obs_noise: float = 0.5, perturb_lm: float = 0.05, perturb_rot: float = 0.002,
               perturb_trans: float = 0.01, normalize_scale: float | None = 100.0) -> BalArrays:
     """Generate a synthetic BAL problem (already in the loaded convention), optionally normalised
@@ -158,6 +182,8 @@ def synth_bal(nc: int, nl: int, mean_n: float, seed: int = 38401, *, max_track: 
     rng = np.random.default_rng(seed)
     # cameras on a ring of radius 10 looking at the origin
     ang = rng.uniform(0.0, 2 * np.pi, nc)
+    if locality > 0:
+        ang = np.sort(ang)  # camera index follows the trajectory
     C = np.stack([10 * np.cos(ang), 10 * np.sin(ang), rng.normal(0, 0.5, nc)], axis=1)
     zc = -C / np.linalg.norm(C, axis=1, keepdims=True)
     up = np.array([0.0, 0.0, 1.0])
@@ -179,7 +205,7 @@ def synth_bal(nc: int, nl: int, mean_n: float, seed: int = 38401, *, max_track: 
     p = 1.0 / (mean_n - 1.0)
     n = 2 + (rng.geometric(p, nl) - 1)
     n = np.minimum(n, min(nc, max_track)).astype(np.int64)
-    obs_cam = _sample_tracks(rng, nc, n)
+    obs_cam = _sample_tracks_local(rng, nc, n, locality) if locality > 0 else _sample_tracks(rng, nc, n)
     lm_of_obs = np.repeat(np.arange(nl), n)
     xy, z, tan = project(cams[obs_cam], lms[lm_of_obs], return_tan=True)
     xy = xy + rng.normal(0, obs_noise, xy.shape)
@@ -219,6 +245,10 @@ def synth_config(name: str, seed: int = 38401, scale: float = 1.0, **kw) -> BalA
     nc, nl, mean_n = CONFIGS[name]
     nc = max(4, int(round(nc * scale)))
     nl = max(8, int(round(nl * scale)))
+    # Ladybug is a vehicle-mounted capture: a track lives in a window of consecutive frames (sequence-like visibility,
+    # which is what makes the reduced camera system ill-conditioned and PCG take tens of iterations).  The photo-collection
+    # sets (Trafalgar, Venice, Final) are clustered but less strictly sequential.
+    kw.setdefault("locality", 2.0 if name.startswith("ladybug") else 6.0)
     return synth_bal(nc, nl, mean_n, seed, **kw)
 
 
