@@ -358,6 +358,13 @@ def bench_ours(args):
         dist.all_reduce(mv_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(mv_bytes, op=dist.ReduceOp.SUM)
     peak, peak_src = hbm_peak()
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same workload), per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_matvec_traffic.json")))
+        if args.workload == "ladybug-1723" and args.scale == 1.0 and args.dtype == "f32" and world == 1:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     achieved = float(mv_bytes.item()) / float(mv_t.item()) / 1e9 / world  # per GPU
     cg_log = [r.get("cg_iterations") for r in st.log[args.warmup:]]
     final_cost = st.log[-1].get("cost")
@@ -407,7 +414,7 @@ def bench_ours(args):
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", [])},
             "roofline": {"bound": "hbm", "kernel": "rcs_matvec (k_matvec_small + k_cam_reduce)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": float(mv_bytes.item()) / world, "us_per_launch": 1e6 * float(mv_t.item())},
             "cpu_baseline": cpu,
             "phases_ms_per_step": {k: 1e3 * v / args.steps for k, v in phase.items()},

@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(256) k_cam_reduce_final(const S* __restrict__ 
   __shared__ int sidx_all[8][SEG_LEN];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
   // the slot indices are constant: stage the first item's before the grid dependency is awaited
   const int it0 = blockIdx.x * wpb + (threadIdx.x >> 5);
   if (it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
@@ -1362,6 +1363,9 @@ __global__ void __launch_bounds__(WARPS * 32, RBA_K4_MINB) k_matvec_small_tma(De
                                                                   const S* __restrict__ xvec, const int* done, int pdl) {
   extern __shared__ __align__(128) unsigned char smem_tma[];
   __shared__ __align__(8) uint64_t bars_all[WARPS][NS];
+  // `done` only ever goes 0 -> 1 inside one solve: if it is already set we may leave before the grid dependency is
+  // resolved (a stale 0 is harmless, the flag is read again after griddepcontrol.wait)
+  if (done && *reinterpret_cast<const volatile int*>(done)) return;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* ring = smem_tma + (size_t)wib * NS * STAGE_BYTES;
   uint64_t* bars = bars_all[wib];
@@ -1527,6 +1531,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
   const int e0 = 9 * cam0, ne = 9 * (cam1 - cam0);
   const bool cached = ne <= VEC_THREADS * VEC_EPT;
   const int cur = i & 1, nxt = cur ^ 1;
+  if (*reinterpret_cast<const volatile int*>(&st->done)) return;  // monotonic flag, see k_matvec_small_tma
   // ---- prefetch of everything that does not depend on the previous kernel of this iteration ----
   S xv[VEC_EPT], rv[VEC_EPT], pv[VEC_EPT], bv[VEC_EPT], qv[VEC_EPT], zv[VEC_EPT], inv[VEC_EPT][9];
   if (cached) {
