@@ -1305,7 +1305,10 @@ __device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const Matve
     const int rows = min(RPS, rows_left);
     const V2* st = reinterpret_cast<const V2*>(ring + (size_t)slot * STAGE_BYTES) + lane;
     int r = 0;
-    for (; r + 2 <= rows; r += 2) {  // two rows at a time: independent dependency chains
+#ifndef RBA_K4_PAIR
+#define RBA_K4_PAIR 0  /* 1: two rows per step (more ILP, 146 registers); 0: one row, 96 registers, 20 warps/SM -- measured equal or better */
+#endif
+    for (; RBA_K4_PAIR && r + 2 <= rows; r += 2) {  // two rows at a time: independent dependency chains
       V2 va[KP], vb[KP];
 #pragma unroll
       for (int k = 0; k < KP; ++k) { va[k] = st[(r * KP + k) * 32]; vb[k] = st[((r + 1) * KP + k) * 32]; }
@@ -1323,7 +1326,7 @@ __device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const Matve
         yv[k].x = fma(db, vb[k].x, yv[k].x); yv[k].y = fma(db, vb[k].y, yv[k].y);
       }
     }
-    if (r < rows) {
+    for (; r < rows; ++r) {
       V2 va[KP];
 #pragma unroll
       for (int k = 0; k < KP; ++k) va[k] = st[(r * KP + k) * 32];
@@ -1355,7 +1358,7 @@ __device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const Matve
 // shared-memory ring (cp.async.bulk + mbarrier complete_tx), so the bytes in flight per SM are set by the
 // ring size (WARPS * NS * STAGE_BYTES) instead of by registers.
 #ifndef RBA_K4_MINB
-#define RBA_K4_MINB 1
+#define RBA_K4_MINB (sizeof(S) == 4 ? 5 : 2)
 #endif
 template <class S, int WARPS, int NS, int STAGE_BYTES>
 __global__ void __launch_bounds__(WARPS * 32, RBA_K4_MINB) k_matvec_small_tma(DevPtrs<S> D, const MatvecItem* __restrict__ items,
