@@ -308,6 +308,11 @@ def bench_ours(args):
                 uid.copy_(torch.frombuffer(bytearray(rb.nccl_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid, 0)
             lin.comm_init(bytes(uid.cpu().numpy().tobytes()))
+            # peer-memory all-reduce fused into the PCG vector kernel: exchange the CUDA IPC handles
+            mine = torch.frombuffer(bytearray(lin.ipc_export()), dtype=torch.uint8).cuda()
+            allh = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            lin.ipc_import(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh))
         return lin
 
     def barrier():

@@ -222,6 +222,11 @@ int32_t rba_synchronize(rba_handle* h);
 int32_t rba_nccl_unique_id(void* out128);
 /* create the communicator for this handle (opts.rank / opts.nranks); collective across ranks */
 int32_t rba_comm_init(rba_handle* h, const void* unique_id128);
+/* Optional (same box, NVLink/NVSwitch peers): fuse the per-PCG-iteration all-reduce of the operator output into the PCG
+ * vector kernel over peer memory.  Every rank exports 128 bytes (two CUDA IPC handles), the host all-gathers them in
+ * rank order and passes the nranks * 128 bytes to every rank.  Without it (or if peer mapping fails) NCCL is used. */
+int32_t rba_ipc_export(rba_handle* h, void* out128);
+int32_t rba_ipc_import(rba_handle* h, const void* all_handles /* nranks * 128 bytes */);
 
 #ifdef __cplusplus
 }

@@ -1522,11 +1522,35 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 constexpr int VEC_THREADS = 512;
 constexpr int VEC_EPT = 2;
+constexpr int MAX_PEERS = 8;
+
+// Peer-memory all-reduce fused into the vector step (multi-GPU): every rank owns a double-buffered y [2][9 nc] and a flag
+// pair in cudaMalloc memory that the other ranks of the box map through CUDA IPC.  A rank publishes its camera-reduced y
+// (written by the previous kernel) by storing the application sequence number into its flag with release.sys semantics,
+// waits for the same number in every peer's flag (acquire.sys over NVLink) and then sums all ranks' y in rank order with
+// L1-bypassing loads, so all ranks obtain bit-identical vectors without a separate collective kernel.
+struct PeerComm {
+  int nranks, rank;
+  const void* y[MAX_PEERS];   // base of rank r's [2][9 nc] buffer (own entry: local pointer)
+  int* flag[MAX_PEERS];       // rank r's [2] sequence flags
+};
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <class S>
+__device__ __forceinline__ S ld_volatile(const S* p) { return *reinterpret_cast<const volatile S*>(p); }
+
 
 template <class S>
 __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState* st, double* part, S lambda, int i, int mode,
-                                                         double eta, int min_it, int is_last, int pdl) {
+                                                         double eta, int min_it, int is_last, int pdl, PeerComm pc, int seq) {
   __shared__ S sr[VEC_THREADS * VEC_EPT + 16];
+  __shared__ int peer_fail;
   const int tid = threadIdx.x;
   const int cams_per_block = (D.nc + gridDim.x - 1) / gridDim.x;
   const int cam0 = min(D.nc, (int)blockIdx.x * cams_per_block);
@@ -1554,6 +1578,34 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
   if (st->done) return;
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double alpha = 0;
+  const bool peers = pc.nranks > 1 && mode != 3;
+  const int slot_off = (seq & 1) * 9 * D.nc;
+  if (peers) {
+    // publish this rank's y (complete: the producing kernel has finished) and wait for every peer's
+    if (tid == 0) peer_fail = 0;
+    if (blockIdx.x == 0 && tid == 0) { __threadfence_system(); st_release_sys(pc.flag[pc.rank] + (seq & 1), seq); }
+    __syncthreads();
+    if (tid < pc.nranks && tid != pc.rank) {
+      const int* f = pc.flag[tid] + (seq & 1);
+      long long spins = 0;
+      while (ld_acquire_sys(f) - seq < 0) {
+        if (++spins > (1LL << 27)) { peer_fail = 1; break; }  // ~seconds: a peer died; fail instead of hanging the GPU
+      }
+    }
+    __syncthreads();
+    if (peer_fail) {  // every CTA sees a failure of its own pollers; the solve is reported as FAILURE
+      if (blockIdx.x == 0 && tid == 0) { st->done = 1; st->term = 2; st->reason = 99; st->iter = i; }
+      return;
+    }
+  }
+  auto load_y = [&](int e) -> S {
+    if (!peers) return __ldcg(D.y + e);
+    S sacc = 0;
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r)
+      if (r < pc.nranks) sacc += ld_volatile(reinterpret_cast<const S*>(pc.y[r]) + slot_off + e);
+    return sacc;
+  };
   if (mode != 3) {
     // ---- P1 ----
     double acc = 0;
@@ -1563,7 +1615,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
         const int l = tid + k * VEC_THREADS;
         if (l < ne) {
           const S vv = (mode == 2) ? xv[k] : pv[k];
-          qv[k] = __ldcg(D.y + e0 + l) + lambda * vv;
+          qv[k] = load_y(e0 + l) + lambda * vv;
           acc += (double)(vv * qv[k]);
         }
       }
@@ -1571,7 +1623,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
       const S* vec = (mode == 2) ? D.x : D.p;
       for (int l = tid; l < ne; l += VEC_THREADS) {
         const S vv = vec[e0 + l];
-        const S q = __ldcg(D.y + e0 + l) + lambda * vv;
+        const S q = load_y(e0 + l) + lambda * vv;
         D.q[e0 + l] = q;
         acc += (double)(vv * q);
       }

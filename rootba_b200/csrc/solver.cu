@@ -62,6 +62,8 @@ struct rba_handle {
   virtual void* stream_ptr() = 0;
   virtual int synchronize() = 0;
   virtual int comm_init(const void* uid) = 0;
+  virtual int ipc_export(void* out128) = 0;
+  virtual int ipc_import(const void* all) = 0;
 };
 
 namespace rba {
@@ -111,11 +113,19 @@ struct Solver : rba_handle {
   // NCCL
   NcclApi* nccl = nullptr;
   ncclComm_t comm = nullptr;
+  // peer-memory all-reduce fused into the PCG vector kernel
+  S* ybuf = nullptr;             // [2][9 nc], IPC-exported
+  int* yflags = nullptr;         // [2] sequence flags, IPC-exported
+  PeerComm pc{};
+  bool peer_ok = false;
+  int ar_seq = 0;
+  std::vector<void*> ipc_opened;
   static constexpr int EBLOCKS = 592;
   static constexpr int KPMAX = sizeof(S) == 4 ? 16 : 10;
 
   ~Solver() override {
     if (comm && nccl) nccl->CommDestroy(comm);
+    for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : allocs) cudaFree(p);
     if (h_state) cudaFreeHost(h_state);
     if (h_red) cudaFreeHost(h_red);
@@ -234,6 +244,8 @@ struct Solver : rba_handle {
     TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
     TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
     TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4)); TRY(dalloc(&d_cam_cnt, (size_t)nc));
+    TRY(dalloc(&ybuf, (size_t)2 * 9 * nc)); TRY(dalloc(&yflags, 4));
+    pc.nranks = 1; pc.rank = opt.rank;
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_state, 1));
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
@@ -348,6 +360,41 @@ struct Solver : rba_handle {
     CU(cudaSetDevice(device));
     ncclResult_t r = nccl->CommInitRank(&comm, opt.nranks, id, opt.rank);
     if (r != ncclSuccess) { g_err = std::string("ncclCommInitRank: ") + nccl->GetErrorString(r); return RBA_ERR_NCCL; }
+    return RBA_OK;
+  }
+
+  int ipc_export(void* out128) override {
+    cudaIpcMemHandle_t hy, hf;
+    CU(cudaIpcGetMemHandle(&hy, ybuf));
+    CU(cudaIpcGetMemHandle(&hf, yflags));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(out128, &hy, 64);
+    std::memcpy((char*)out128 + 64, &hf, 64);
+    return RBA_OK;
+  }
+  int ipc_import(const void* all) override {
+    if (opt.nranks == 1) return RBA_OK;
+    if (opt.nranks > MAX_PEERS) { g_err = "peer all-reduce supports at most 8 ranks"; return RBA_ERR_UNSUPPORTED; }
+    if (const char* e = getenv("RBA_PEER_AR")) if (atoi(e) == 0) return RBA_OK;
+    CU(cudaSetDevice(device));
+    pc.nranks = opt.nranks; pc.rank = opt.rank;
+    for (int r = 0; r < opt.nranks; ++r) {
+      if (r == opt.rank) { pc.y[r] = ybuf; pc.flag[r] = yflags; continue; }
+      cudaIpcMemHandle_t hy, hf;
+      std::memcpy(&hy, (const char*)all + (size_t)128 * r, 64);
+      std::memcpy(&hf, (const char*)all + (size_t)128 * r + 64, 64);
+      void *py = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&py, hy, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        pc.nranks = 1;  // fall back to NCCL for the operator all-reduce
+        g_err = "cudaIpcOpenMemHandle failed; using NCCL for the PCG all-reduce";
+        return RBA_OK;
+      }
+      ipc_opened.push_back(py); ipc_opened.push_back(pf);
+      pc.y[r] = py; pc.flag[r] = (int*)pf;
+    }
+    peer_ok = true;
     return RBA_OK;
   }
 
@@ -492,16 +539,22 @@ struct Solver : rba_handle {
     }
     ++tm.matvec_launches;
   }
-  int pcg_vec(int i, int mode, bool pdl, int is_last, S lambda) {
+  int pcg_vec(int i, int mode, bool pdl, int is_last, S lambda, bool fused_ar = false) {
+    PeerComm c = pc;
+    if (!fused_ar) c.nranks = 1;
     return launch_ex(k_pcg_vec<S>, pcg_cluster, VEC_THREADS, 0, pdl && use_pdl, pcg_cluster, D, d_state, d_part4, lambda, i, mode, (double)opt.eta,
-                     (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl));
+                     (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl), c, ar_seq);
   }
   // finish one operator application inside PCG (H v for v = p in mode 0/1, x in mode 2) and do the vector step
   int pcg_apply(int i, int mode, int is_last, S lambda) {
+    const bool fused = opt.nranks > 1 && peer_ok;
+    if (fused) ++ar_seq;
+    S* ydst = fused ? ybuf + (size_t)(ar_seq & 1) * 9 * nc : D.y;
     int rc = launch_ex(k_cam_reduce_final<S>, grid_for(n_y_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, (const int*)d_csr_y_slots,
-                       (const ReduceItem*)d_csr_y_items, n_y_items, (const int*)d_csr_y_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl);
+                       (const ReduceItem*)d_csr_y_items, n_y_items, (const int*)d_csr_y_item_ptr, D.partial, d_cam_cnt, ydst, (const int*)&d_state->done, (int)use_pdl);
     if (rc) return rc;
     if (opt.nranks == 1) return pcg_vec(i, mode, true, is_last, lambda);
+    if (fused) return pcg_vec(i, mode, true, is_last, lambda, true);
     rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
     return pcg_vec(i, mode, false, is_last, lambda);
   }
@@ -825,5 +878,7 @@ int32_t rba_nccl_unique_id(void* out128) {
   return RBA_OK;
 }
 int32_t rba_comm_init(rba_handle* h, const void* uid) { return h->comm_init(uid); }
+int32_t rba_ipc_export(rba_handle* h, void* out128) { return h->ipc_export(out128); }
+int32_t rba_ipc_import(rba_handle* h, const void* all) { return h->ipc_import(all); }
 
 }  // extern "C"

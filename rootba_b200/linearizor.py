@@ -179,6 +179,15 @@ class LinearizorQR:
         buf = C.create_string_buffer(unique_id, 128)
         check(_lib.lib().rba_comm_init(self.h, buf))
 
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_lib.lib().rba_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_import(self, all_handles: bytes):
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        check(_lib.lib().rba_ipc_import(self.h, buf))
+
     # ---- Linearizor interface ----
     def start_iteration(self, it_summary: dict | None = None):
         self.it_summary = it_summary
