@@ -151,6 +151,12 @@ int32_t rba_scalar_size(const rba_handle* h);
 int32_t rba_partition_landmarks(int32_t num_landmarks, const int64_t* lm_obs_offset, int32_t nranks,
                                 int32_t* bounds);
 
+/* Host-only self check of the data model built for (problem, rank, nranks): every observation is assigned to exactly one
+ * slot with the right camera, tiles are homogeneous in track length, the matvec row chunks tile every panel exactly once,
+ * the camera-major CSRs list every (y) slot exactly once under its camera, shards cover the landmarks.  Needs no GPU.
+ * scalar_size selects the float (4) or double (8) class limits.  Returns RBA_OK or RBA_ERR_STATE (see rba_last_error). */
+int32_t rba_layout_selftest(const rba_problem_view* problem, int32_t rank, int32_t nranks, int32_t scalar_size);
+
 /* ---- optimisation state: BalProblem cameras()/landmarks() mirror ------------------------- */
 
 /* host -> device; cams [10*Nc], lms [3*Nl] (full problem; a sharded handle reads its slice) */

@@ -838,6 +838,91 @@ int32_t rba_partition_landmarks(int32_t nl, const int64_t* off, int32_t nranks, 
   return RBA_OK;
 }
 
+int32_t rba_layout_selftest(const rba_problem_view* pv, int32_t rank, int32_t nranks, int32_t scalar_size) {
+  using namespace rba;
+  if (!pv || nranks < 1 || rank < 0 || rank >= nranks) { g_err = "bad arguments"; return RBA_ERR_INVALID_ARGUMENT; }
+  Layout L;
+  std::string msg = build_layout(pv->num_cameras, pv->num_landmarks, pv->lm_obs_offset, pv->obs_cam_idx, rank, nranks, scalar_size == 4 ? 16 : 10, L);
+  if (!msg.empty()) { g_err = msg; return RBA_ERR_INVALID_ARGUMENT; }
+  auto fail = [&](const std::string& m) { g_err = "layout selftest: " + m; return RBA_ERR_STATE; };
+  // observations <-> slots
+  std::vector<char> seen((size_t)L.nobs_local, 0);
+  const int64_t obs0 = pv->lm_obs_offset[L.lm_begin];
+  long long real_slots = 0;
+  for (int s = 0; s < L.nslots; ++s) {
+    if (L.slot_lm[s] < 0) { if (L.slot_obs[s] >= 0) return fail("padding slot with an observation"); continue; }
+    const long long o = L.slot_obs[s];
+    if (o < obs0 || o - obs0 >= L.nobs_local) return fail("slot observation outside the shard");
+    if (seen[o - obs0]++) return fail("observation assigned twice");
+    if (pv->obs_cam_idx[o] != L.slot_cam[s]) return fail("slot camera mismatch");
+    const int lm = L.lm_begin + L.slot_lm[s];
+    if (o < pv->lm_obs_offset[lm] || o >= pv->lm_obs_offset[lm + 1]) return fail("slot landmark mismatch");
+    ++real_slots;
+  }
+  if (real_slots != L.nobs_local) return fail("not every observation has a slot");
+  // tiles
+  std::vector<char> lm_seen((size_t)L.nl_local, 0);
+  long long panel = 0;
+  for (size_t t = 0; t < L.tiles.size(); ++t) {
+    const TileInfo& T = L.tiles[t];
+    const int W = 32 / T.G;
+    if (T.G != group_size_for(T.n) || T.KP != kp_for(T.n, T.G) || 2 * T.G * T.KP < 9 * T.n) return fail("tile class");
+    if (T.panel_off != panel) return fail("panel offsets are not contiguous");
+    panel += (long long)2 * T.n * T.KP * 64;
+    for (int g = 0; g < W; ++g) {
+      const int lm = L.sorted_lm[T.lm_base + g];
+      if ((g < T.nvalid) != (lm >= 0)) return fail("nvalid");
+      if (lm < 0) continue;
+      if (lm_seen[lm]++) return fail("landmark in two tiles");
+      if (pv->lm_obs_offset[L.lm_begin + lm + 1] - pv->lm_obs_offset[L.lm_begin + lm] != T.n) return fail("track length of tile");
+      for (int i = 0; i < T.n; ++i) {
+        const int s = T.slot_base + g * T.n + i;
+        if (L.slot_lm[s] != lm || L.slot_obs[s] != pv->lm_obs_offset[L.lm_begin + lm] + i) return fail("slot order inside a landmark");
+      }
+      if (L.sorted_of_lm[lm] != T.lm_base + g) return fail("sorted_of_lm");
+    }
+  }
+  if (panel != L.panel_scalars) return fail("panel size");
+  for (char c : lm_seen) if (!c) return fail("landmark without tile");
+  // matvec items: row chunks tile [0, 2n) of every tile exactly once; y slots
+  std::vector<int> rows_covered(L.tiles.size(), 0);
+  std::vector<char> yslot_used((size_t)L.nyslots, 0);
+  for (const MatvecItem& it : L.items) {
+    const TileInfo& T = L.tiles[it.tile];
+    if (it.nrows <= 0 || it.row0 < 0 || it.row0 + it.nrows > 2 * T.n) return fail("item rows");
+    rows_covered[it.tile] += it.nrows;
+    for (int k = 0; k < (32 / T.G) * T.n; ++k) {
+      if (it.yslot_base + k >= L.nyslots) return fail("y slot range");
+      if (yslot_used[it.yslot_base + k]++) return fail("y slot written by two items");
+    }
+  }
+  for (size_t t = 0; t < L.tiles.size(); ++t) if (rows_covered[t] != 2 * L.tiles[t].n) return fail("rows not covered exactly once");
+  // camera CSRs
+  auto check_csr = [&](const CameraCSR& C, long long expect) -> bool {
+    if ((long long)C.slots.size() != expect) return false;
+    for (int c = 0; c < pv->num_cameras; ++c) {
+      for (int e = C.cam_ptr[c]; e < C.cam_ptr[c + 1]; ++e) if (e > C.cam_ptr[c] && C.slots[e] <= C.slots[e - 1]) return false;
+      int covered = 0;
+      for (int q = C.cam_item_ptr[c]; q < C.cam_item_ptr[c + 1]; ++q) {
+        if (C.items[q].cam != c || C.items[q].begin != C.cam_ptr[c] + covered) return false;
+        covered += C.items[q].end - C.items[q].begin;
+      }
+      if (covered != C.cam_ptr[c + 1] - C.cam_ptr[c]) return false;
+    }
+    return true;
+  };
+  if (!check_csr(L.csr_obs, L.nobs_local)) return fail("observation CSR");
+  for (int c = 0; c < pv->num_cameras; ++c)
+    for (int e = L.csr_obs.cam_ptr[c]; e < L.csr_obs.cam_ptr[c + 1]; ++e)
+      if (L.slot_cam[L.csr_obs.slots[e]] != c || L.slot_lm[L.csr_obs.slots[e]] < 0) return fail("observation CSR camera");
+  if (!L.csr_y_is_obs) {
+    long long expect = 0;
+    for (const MatvecItem& it : L.items) expect += (long long)L.tiles[it.tile].nvalid * L.tiles[it.tile].n;
+    if (!check_csr(L.csr_y, expect)) return fail("y CSR");
+  }
+  return RBA_OK;
+}
+
 int32_t rba_set_state(rba_handle* h, const void* cams, const void* lms) { return h->set_state(cams, lms); }
 int32_t rba_get_state(rba_handle* h, void* cams, void* lms) { return h->get_state(cams, lms); }
 int32_t rba_backup(rba_handle* h) { return h->backup(); }

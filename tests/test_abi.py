@@ -46,3 +46,37 @@ def test_default_opts_match_reference_defaults():
     # bal/solver_options.hpp: SCHUR_JACOBI, max 500 its, eta 0.1, Householder
     assert (o.preconditioner_type, o.max_linear_solver_iterations, o.eta, o.use_householder_marginalization) == (1, 500, 0.1, 1)
     assert o.residual_reset_period == 10 and o.nranks == 1
+
+
+@pytest.mark.parametrize("shape", [(12, 300, 4.1, 400), (150, 1500, 9.0, 150), (300, 120, 60.0, 300), (9, 77, 2.0001, 400)])
+def test_layout_selftest(shape):
+    """indexing is bit-exact: every observation lands in exactly one slot with its camera, row chunks tile every panel
+    once, the camera-major CSRs cover every slot once, for 1, 2, 3 and 8 shards and both scalar classes"""
+    from rootba_b200.synthetic import synth_bal
+    nc, nl, mean_n, max_track = shape
+    a = synth_bal(nc, nl, mean_n, seed=3, max_track=max_track)
+    L = _lib.lib()
+    off = np.ascontiguousarray(a.lm_off, np.int64)
+    oc = np.ascontiguousarray(a.obs_cam, np.int32)
+    xy = np.ascontiguousarray(a.obs_xy, np.float64)
+    pv = _lib.ProblemView(a.nc, a.nl, a.nobs, off.ctypes.data, oc.ctypes.data, xy.ctypes.data)
+    for nranks in (1, 2, 3, 8):
+        for rank in range(nranks):
+            for ssz in (4, 8):
+                rc = L.rba_layout_selftest(C.byref(pv), rank, nranks, ssz)
+                assert rc == 0, (nranks, rank, ssz, L.rba_last_error())
+
+
+def test_layout_rejects_unsorted_and_short_tracks(tiny_problem):
+    a = tiny_problem
+    L = _lib.lib()
+    off = np.ascontiguousarray(a.lm_off, np.int64)
+    xy = np.ascontiguousarray(a.obs_xy, np.float64)
+    oc = np.ascontiguousarray(a.obs_cam, np.int32).copy()
+    oc[[0, 1]] = oc[[1, 0]]  # first landmark no longer ascending
+    pv = _lib.ProblemView(a.nc, a.nl, a.nobs, off.ctypes.data, oc.ctypes.data, xy.ctypes.data)
+    assert L.rba_layout_selftest(C.byref(pv), 0, 1, 8) != 0
+    off2 = off.copy(); off2[1] = off2[0] + 1  # a landmark with one observation (reference: LOG(FATAL), ipp:73-76)
+    oc2 = np.ascontiguousarray(a.obs_cam, np.int32)
+    pv2 = _lib.ProblemView(a.nc, a.nl, a.nobs, off2.ctypes.data, oc2.ctypes.data, xy.ctypes.data)
+    assert L.rba_layout_selftest(C.byref(pv2), 0, 1, 8) != 0
