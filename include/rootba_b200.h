@@ -60,7 +60,7 @@ typedef struct {
 
 /* Subset of SolverOptions (bal/solver_options.hpp:46-284) read by the QR path, plus placement. */
 typedef struct {
-  int32_t use_householder_marginalization; /* :258 ; only 1 is implemented on device (0 -> RBA_ERR_UNSUPPORTED) */
+  int32_t use_householder_marginalization; /* :258 ; 1 = Householder (ipp:717-743), 0 = Givens (ipp:700-715); both run on the device */
   int32_t use_valid_projections_only;      /* SolverOptions::use_projection_validity_check() */
   int32_t robust_norm;                     /* 0 NONE, 1 HUBER  (bal_residual_options.hpp:52) */
   double huber_parameter;                  /* bal_residual_options.hpp:58 */

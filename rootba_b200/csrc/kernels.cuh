@@ -504,6 +504,31 @@ __device__ __forceinline__ S* scratch_ptr(const Scratch<S>& sc, S* smem_warp, in
   return sc.gbase + w * sc.gstride;
 }
 
+template <class S>
+struct Rot { S c, s; };
+
+template <class S>
+__device__ __forceinline__ Rot<S> make_givens(S p, S q) {  // Eigen JacobiRotation::makeGivens (SURVEY A8)
+  Rot<S> g;
+  if (q == S(0)) { g.c = p < S(0) ? S(-1) : S(1); g.s = 0; }
+  else if (p == S(0)) { g.c = 0; g.s = q < S(0) ? S(1) : S(-1); }
+  else if (fabs(p) > fabs(q)) {
+    const S t = q / p; S u = sqrt(S(1) + t * t); if (p < S(0)) u = -u;
+    g.c = S(1) / u; g.s = -t * g.c;
+  } else {
+    const S t = p / q; S u = sqrt(S(1) + t * t); if (q < S(0)) u = -u;
+    g.s = -S(1) / u; g.c = -t * g.s;
+  }
+  return g;
+}
+// applyOnTheLeft(p=damping row, q=row n): x' = c x + s y ; y' = -s x + c y
+template <class S>
+__device__ __forceinline__ void rot_apply(const Rot<S>& g, S& x, S& y) {
+  const S xi = x, yi = y;
+  x = g.c * xi + g.s * yi;
+  y = -g.s * xi + g.c * yi;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1b  linearize + Jl scaling + Householder QR of the 3 landmark columns + write marginalised panel
 //   ref: ipp:88-147 (linearize_landmark), :571-587 (scale_Jl_cols), :717-743 (perform_qr_householder),
@@ -514,7 +539,7 @@ __device__ __forceinline__ S* scratch_ptr(const Scratch<S>& sc, S* smem_warp, in
 //   block-diagonal Jp through their compact-WY form, one output element = 3 FMAs, written straight into
 //   the coalesced panel layout.
 // ------------------------------------------------------------------------------------------------
-template <class S>
+template <class S, bool GIVENS>
 __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scratch<S> sc, int* bad_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using V2 = typename ST<S>::V2;
@@ -622,10 +647,33 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
     __syncwarp();
     // ---- c. Householder QR of A = [Jl | r] (2n x 4), rows rho = 2i + parity ----
 #define A_AT(rho, c) sJ[26 * ((rho) >> 1) + ((c) < 3 ? 18 + 3 * ((rho)&1) + (c) : 24 + ((rho)&1))]
-    S tau[3];
+    S tau[3] = {0, 0, 0};
     const int nrows = 2 * n;
+    if constexpr (GIVENS) {
+      // perform_qr_givens (ref: ipp:700-715): for column k the adjacent-row rotations (m-1, m), m = 2n-1 .. k+1, are a
+      // sequential chain (each uses the entry the previous one produced): one lane per landmark runs it on the 2n x 4
+      // matrix and keeps every (c, s): c in sV[3m + k], s in the entry A(m, k) the rotation has just annihilated.
+      // (The reference rotates full rows, i.e. also the ~0 leftovers in columns < k; nothing downstream reads them.)
+      if (j == 0) {
 #pragma unroll 1
-    for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll 1
+          for (int m = nrows - 1; m > k; --m) {
+            const Rot<S> gr = make_givens(A_AT(m - 1, k), A_AT(m, k));
+            for (int c = k; c < 4; ++c) {
+              S x = A_AT(m, c), y = A_AT(m - 1, c);
+              rot_apply(gr, x, y);  // applyOnTheLeft(m, m-1, gr)
+              A_AT(m, c) = x; A_AT(m - 1, c) = y;
+            }
+            sV[3 * m + k] = gr.c;
+            A_AT(m, k) = gr.s;
+          }
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int k = 0; k < (GIVENS ? 0 : 3); ++k) {
       S ts = 0;
       for (int rho = j; rho < nrows; rho += G)
         if (rho > k) { const S v = A_AT(rho, k); ts += v * v; }
@@ -677,11 +725,13 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
       __syncwarp();
     }
     S g10 = 0, g20 = 0, g21 = 0;
-    for (int rho = j; rho < nrows; rho += G) {
-      const S v0 = sV[3 * rho], v1 = sV[3 * rho + 1], v2 = sV[3 * rho + 2];
-      g10 += v1 * v0; g20 += v2 * v0; g21 += v2 * v1;
+    if constexpr (!GIVENS) {
+      for (int rho = j; rho < nrows; rho += G) {
+        const S v0 = sV[3 * rho], v1 = sV[3 * rho + 1], v2 = sV[3 * rho + 2];
+        g10 += v1 * v0; g20 += v2 * v0; g21 += v2 * v1;
+      }
+      g10 = group_sum(g10, G); g20 = group_sum(g20, G); g21 = group_sum(g21, G);
     }
-    g10 = group_sum(g10, G); g20 = group_sum(g20, G); g21 = group_sum(g21, G);
     if (active && j == 0) {
       S* lk = D.lmk + 24 * (size_t)sidx;
       lk[0] = A_AT(0, 0); lk[1] = A_AT(0, 1); lk[2] = A_AT(0, 2);
@@ -689,12 +739,81 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
       lk[6] = A_AT(0, 3); lk[7] = A_AT(1, 3); lk[8] = A_AT(2, 3);
       lk[18] = jls[0]; lk[19] = jls[1]; lk[20] = jls[2];
     }
-#undef A_AT
     // ---- d. apply Q^T = H2 H1 H0 to the block-diagonal Jp (compact WY) and write q1u + panel ----
     V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off);
     const int ncols = 9 * n;
+    if constexpr (GIVENS) {
+      // Each panel column is an independent 2n-vector (non-zero in rows 2i, 2i+1 only) that goes through the same three
+      // rotation chains.  Chain k at rotation m needs row m-1 as left by chain k-1, which chain k-1 finishes one step
+      // later, so one descending sweep runs the three chains with a lag of one row each:
+      //   step t: chain 0 does rotation t, chain 1 rotation t+1, chain 2 rotation t+2 (= final row t+2).
+      const int R = nrows - 1;
 #pragma unroll 1
-    for (int k = 0; k < KP; ++k) {
+      for (int k = 0; k < KP; ++k) {
+        const int c0 = 2 * j + 2 * G * k;
+        S a0[2], a1[2], cur0[2], cur1[2] = {0, 0}, cur2[2] = {0, 0};
+        int r2i[2], oi[2], op[2];
+        bool vc[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int c = c0 + v;
+          vc[v] = c < ncols;
+          const int i = vc[v] ? c / 9 : 0;
+          const int p = vc[v] ? c - 9 * i : 0;
+          oi[v] = i; op[v] = p; r2i[v] = 2 * i;
+          a0[v] = vc[v] ? sJ[26 * i + p] : S(0);
+          a1[v] = vc[v] ? sJ[26 * i + 9 + p] : S(0);
+          cur0[v] = (R == r2i[v] + 1) ? a1[v] : S(0);
+        }
+        V2* pk = ptile + (size_t)k * 32 + lane;
+#pragma unroll 1
+        for (int t = R; t >= 1; --t) {
+          const Rot<S> g0{sV[3 * t], A_AT(t, 0)};
+          S o0[2], o1[2] = {0, 0};
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            S y = (t - 1 == r2i[v]) ? a0[v] : ((t - 1 == r2i[v] + 1) ? a1[v] : S(0));
+            o0[v] = cur0[v];
+            rot_apply(g0, o0[v], y);
+            cur0[v] = y;
+          }
+          if (t == R) {
+            cur1[0] = o0[0]; cur1[1] = o0[1];
+            continue;
+          }
+          const Rot<S> g1{sV[3 * (t + 1) + 1], A_AT(t + 1, 1)};
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            S y = o0[v];
+            o1[v] = cur1[v];
+            rot_apply(g1, o1[v], y);
+            cur1[v] = y;
+          }
+          if (t == R - 1) {
+            cur2[0] = o1[0]; cur2[1] = o1[1];
+            continue;
+          }
+          const Rot<S> g2{sV[3 * (t + 2) + 2], A_AT(t + 2, 2)};
+          S f[2];
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            S y = o1[v];
+            f[v] = cur2[v];
+            rot_apply(g2, f[v], y);
+            cur2[v] = y;
+          }
+          if (active) pk[(size_t)(t + 2 - 3) * KP * 32] = mk2(vc[0] ? f[0] : S(0), vc[1] ? f[1] : S(0));
+        }
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+          if (vc[v]) {
+            S* q = sQ + 28 * (g * n + oi[v]) + op[v];
+            q[0] = cur0[v]; q[9] = cur1[v]; q[18] = cur2[v];
+          }
+      }
+    }
+#pragma unroll 1
+    for (int k = 0; k < (GIVENS ? 0 : KP); ++k) {
       const int c0 = 2 * j + 2 * G * k;
       S a0[2], a1[2], w0[2], w1[2], w2[2];
       int r2i[2], oi[2], op[2];
@@ -754,6 +873,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
         }
       }
     }
+#undef A_AT
     for (int e = lane; e < Wn; e += 32) sQ[28 * e + 27] = 0;  // pad
     __syncwarp();
     warp_copy_out(D.q1u + 28 * (size_t)T.slot_base, sQ, T.nvalid * n * 28, lane);
@@ -768,30 +888,6 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
 //   un-doing the previous rotations, ipp:175-186).  The gradient uses orthogonality of [Q1d; P]:
 //   P^T (Q2^T r) = Jp^T r - Q1d^T (Q1^T r)_d.
 // ------------------------------------------------------------------------------------------------
-template <class S>
-struct Rot { S c, s; };
-
-template <class S>
-__device__ __forceinline__ Rot<S> make_givens(S p, S q) {  // Eigen JacobiRotation::makeGivens (SURVEY A8)
-  Rot<S> g;
-  if (q == S(0)) { g.c = p < S(0) ? S(-1) : S(1); g.s = 0; }
-  else if (p == S(0)) { g.c = 0; g.s = q < S(0) ? S(1) : S(-1); }
-  else if (fabs(p) > fabs(q)) {
-    const S t = q / p; S u = sqrt(S(1) + t * t); if (p < S(0)) u = -u;
-    g.c = S(1) / u; g.s = -t * g.c;
-  } else {
-    const S t = p / q; S u = sqrt(S(1) + t * t); if (q < S(0)) u = -u;
-    g.s = -S(1) / u; g.c = -t * g.s;
-  }
-  return g;
-}
-// applyOnTheLeft(p=damping row, q=row n): x' = c x + s y ; y' = -s x + c y
-template <class S>
-__device__ __forceinline__ void rot_apply(const Rot<S>& g, S& x, S& y) {
-  const S xi = x, yi = y;
-  x = g.c * xi + g.s * yi;
-  y = -g.s * xi + g.c * yi;
-}
 
 // scratch scalars per warp for a tile (host mirrors this in Solver::init)
 __host__ __device__ inline int stage2_need(int n, int G, int KP) {

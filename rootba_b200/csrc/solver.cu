@@ -170,7 +170,6 @@ struct Solver : rba_handle {
   int init(const rba_problem_view* pv, const rba_solver_opts* o) {
     opt = *o;
     if (opt.nranks < 1 || opt.rank < 0 || opt.rank >= opt.nranks) { g_err = "bad rank/nranks"; return RBA_ERR_INVALID_ARGUMENT; }
-    if (!opt.use_householder_marginalization) { g_err = "Givens marginalisation is not implemented on device"; return RBA_ERR_UNSUPPORTED; }
     if (opt.pcg_check_period <= 0) opt.pcg_check_period = 4;
     if (opt.residual_reset_period <= 0) opt.residual_reset_period = 10;
     int ndev = 0;
@@ -277,7 +276,8 @@ struct Solver : rba_handle {
       };
       TRY(setup(k1_sc, K1_CAP, need1, k1_smem, k1_bps, k1_max_blocks));
       TRY(setup(k2_sc, K2_CAP, need2, k2_smem, k2_bps, k2_max_blocks));
-      CU(cudaFuncSetAttribute(k_linearize_qr<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
+      CU(cudaFuncSetAttribute((k_linearize_qr<S, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
+      CU(cudaFuncSetAttribute((k_linearize_qr<S, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
       CU(cudaFuncSetAttribute(k_stage2<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
     }
     k4_smem_small = (size_t)K4_WARPS * L.k4_scratch_per_warp * sizeof(S);
@@ -485,7 +485,10 @@ struct Solver : rba_handle {
     rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.diag2, nullptr); if (rc) return rc;
     k_scaling<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.diag2, D.scaling, 9 * nc, (S)ko.jacobi_eps);
     // pass B: linearize (scaled) + Jl scaling + Householder QR + panel write
-    k_linearize_qr<S><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags);
+    if (opt.use_householder_marginalization)
+      k_linearize_qr<S, false><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags);
+    else  // ref: ipp:149-163 selects perform_qr_givens
+      k_linearize_qr<S, true><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags);
     launches += 2;
     if (opt.preconditioner_type == 0) {
       // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)

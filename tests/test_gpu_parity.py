@@ -33,6 +33,9 @@ def make_pair(arrays, dtype, **opt_kw):
         so.optimized_cost = opt_kw["optimized_cost"]
         okw["optimized_cost"] = {"ERROR": 0, "ERROR_VALID": 1, "ERROR_VALID_AVG": 2}[so.optimized_cost]
         okw["use_valid_projections_only"] = int(so.use_projection_validity_check())
+    if "use_householder_marginalization" in opt_kw:
+        so.use_householder_marginalization = bool(opt_kw["use_householder_marginalization"])
+        okw["use_householder"] = int(so.use_householder_marginalization)
     if "max_num_iterations" in opt_kw:
         so.max_num_iterations = okw["max_num_iterations"] = opt_kw["max_num_iterations"]
     bp = rb.BalProblem.from_arrays(arrays, dtype)
@@ -69,9 +72,10 @@ def test_compute_error(small_problem, dtype):
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("which", ["small", "mixed"])
-def test_stage_parity(small_problem, mixed_problem, dtype, which):
+@pytest.mark.parametrize("qr", ["householder", "givens"])  # ref: ipp:717-743 (default) / ipp:700-715
+def test_stage_parity(small_problem, mixed_problem, dtype, which, qr):
     arrays = small_problem if which == "small" else mixed_problem
-    bp, lin, o, _ = make_pair(arrays, dtype)
+    bp, lin, o, _ = make_pair(arrays, dtype, use_householder_marginalization=(qr == "householder"))
     tol = TOL1[dtype]
     lam = 0.1
     lin.linearize()
@@ -156,6 +160,7 @@ def test_backup_restore(small_problem):
     (np.float64, {"preconditioner_type": "JACOBI"}),
     (np.float32, {"robust_norm": "HUBER", "huber_parameter": 2.0}),
     (np.float64, {"optimized_cost": "ERROR_VALID"}),
+    (np.float64, {"use_householder_marginalization": False}),
 ])
 def test_lm_trajectory(small_problem, dtype, kw):
     import rootba_b200 as rb
@@ -199,8 +204,8 @@ def test_long_tracks_generic_path():
     from rootba_b200.synthetic import synth_bal
     arrays = synth_bal(300, 120, 60.0, seed=4, max_track=300)
     assert arrays.track_lengths().max() > 113
-    for dtype in (np.float32, np.float64):
-        bp, lin, o, _ = make_pair(arrays, dtype)
+    for dtype, hh in ((np.float32, True), (np.float64, True), (np.float64, False)):
+        bp, lin, o, _ = make_pair(arrays, dtype, use_householder_marginalization=hh)
         lin.linearize(); assert o.linearize()
         inc_g = lin.solve(0.01)
         inc_c, _ = o.solve(0.01)
