@@ -77,7 +77,7 @@ struct Options {
   double initial_trust_region_radius = 1e4;  // :152
   double min_trust_region_radius = 1e-32;  // :157
   double max_trust_region_radius = 1e16;   // :163
-  double min_relative_decrease = 1e-3;     // :170
+  double min_relative_decrease = 0;        // bal/solver_options.hpp:146-148 (reference default 0; Ceres uses 1e-3)
   double function_tolerance = 1e-6;        // :238
   double initial_vee = 2.0;                // :274
   double vee_factor = 2.0;                 // :278

@@ -25,7 +25,7 @@ struct SolverOptions {
   enum class RobustNorm { NONE = 0, HUBER = 1 };
   OptimizedCost optimized_cost = OptimizedCost::ERROR;
   int max_num_iterations = 20;
-  double min_relative_decrease = 1e-3;
+  double min_relative_decrease = 0;  // solver_options.hpp:146-148
   double initial_trust_region_radius = 1e4;
   double min_trust_region_radius = 1e-32;
   double max_trust_region_radius = 1e16;

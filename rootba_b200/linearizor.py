@@ -33,7 +33,7 @@ class SolverOptions:  # bal/solver_options.hpp (QR-relevant subset, reference de
     solver_type: str = "SQUARE_ROOT"
     optimized_cost: str = "ERROR"                 # ERROR | ERROR_VALID | ERROR_VALID_AVG
     max_num_iterations: int = 20
-    min_relative_decrease: float = 1e-3
+    min_relative_decrease: float = 0.0           # solver_options.hpp:146-148
     initial_trust_region_radius: float = 1e4
     min_trust_region_radius: float = 1e-32
     max_trust_region_radius: float = 1e16
