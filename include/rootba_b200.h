@@ -157,6 +157,27 @@ int32_t rba_partition_landmarks(int32_t num_landmarks, const int64_t* lm_obs_off
  * scalar_size selects the float (4) or double (8) class limits.  Returns RBA_OK or RBA_ERR_STATE (see rba_last_error). */
 int32_t rba_layout_selftest(const rba_problem_view* problem, int32_t rank, int32_t nranks, int32_t scalar_size);
 
+/* ---- BAL file loader (host only, no GPU) ----------------------------------- */
+
+/* load_normalized_bal_problem (bal/bal_problem.cpp:773-852) = load_bal (:189-282: whitespace-separated
+ * "Nc Nl Nobs", Nobs x (cam lm x y), 9 values per camera, 3 per landmark; y of the image and y/z of the camera frame
+ * flipped; observations of a landmark in ascending camera order like the reference's std::map, bal_problem.hpp:137;
+ * duplicate observation / short or malformed file -> RBA_ERR_INVALID_ARGUMENT where the reference LOG(FATAL)s)
+ * + normalize(scale) (:428-469, median-centre + MAD-scale, in double) when `normalize` != 0.
+ * The file is parsed by `num_threads` threads (<= 0: all hardware threads) straight into the flat arrays of
+ * rba_problem_view; the result is bit-identical to a one-fscanf-per-line loader (from_chars and "%lf" both round
+ * correctly).  All values are double, as in the reference (cast to float happens after normalisation, :813-832). */
+typedef struct rba_bal_file rba_bal_file;
+int32_t rba_bal_load(const char* path, int32_t normalize, double scale, int32_t num_threads, rba_bal_file** out);
+/* sizes, to allocate the arrays for rba_bal_copy */
+int32_t rba_bal_dims(const rba_bal_file* f, int32_t* num_cameras, int32_t* num_landmarks, int64_t* num_observations);
+/* cams [10*Nc] (qx,qy,qz,qw,t,f,k1,k2 = Camera::params(), bal_problem.hpp:84-89), lms [3*Nl], lm_obs_offset [Nl+1],
+ * obs_cam_idx [Nobs], obs_xy [2*Nobs]; any pointer may be NULL */
+int32_t rba_bal_copy(const rba_bal_file* f, double* cams, double* lms, int64_t* lm_obs_offset, int32_t* obs_cam_idx, double* obs_xy);
+/* seconds spent reading / counting tokens / parsing / building the CSR / normalising in rba_bal_load */
+int32_t rba_bal_load_timings(const rba_bal_file* f, double* out5);
+int32_t rba_bal_free(rba_bal_file* f);
+
 /* ---- optimisation state: BalProblem cameras()/landmarks() mirror ------------------------- */
 
 /* host -> device; cams [10*Nc], lms [3*Nl] (full problem; a sharded handle reads its slice) */

@@ -7,11 +7,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <limits>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/rootba_b200.h"
+#include "../host/bal_io_fast.hpp"
 #include "kernels.cuh"
 #include "nccl_dyn.hpp"
 
@@ -840,6 +843,53 @@ int32_t rba_partition_landmarks(int32_t nl, const int64_t* off, int32_t nranks, 
   rba::partition_landmarks(nl, off, nranks, bounds);
   return RBA_OK;
 }
+
+// ---- BAL loader (host only) ----
+struct rba_bal_file {
+  rootba_b200::BalProblemSoA<double> p;
+  double timings[5] = {0, 0, 0, 0, 0};
+};
+
+int32_t rba_bal_load(const char* path, int32_t normalize, double scale, int32_t num_threads, rba_bal_file** out) {
+  if (!path || !out) { rba::g_err = "bad arguments"; return RBA_ERR_INVALID_ARGUMENT; }
+  *out = nullptr;
+  try {
+    std::unique_ptr<rba_bal_file> f(new rba_bal_file());
+    rootba_b200::LoadTimings t;
+    f->p = rootba_b200::load_bal_parallel(path, num_threads, &t);
+    const auto t0 = std::chrono::steady_clock::now();
+    if (normalize) f->p.normalize(scale);
+    f->timings[0] = t.read; f->timings[1] = t.count; f->timings[2] = t.parse; f->timings[3] = t.csr;
+    f->timings[4] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *out = f.release();
+    return RBA_OK;
+  } catch (const std::exception& e) {
+    rba::g_err = e.what();
+    return RBA_ERR_INVALID_ARGUMENT;
+  }
+}
+int32_t rba_bal_dims(const rba_bal_file* f, int32_t* nc, int32_t* nl, int64_t* nobs) {
+  if (!f) return RBA_ERR_INVALID_ARGUMENT;
+  if (nc) *nc = f->p.nc;
+  if (nl) *nl = f->p.nl;
+  if (nobs) *nobs = f->p.num_observations();
+  return RBA_OK;
+}
+int32_t rba_bal_copy(const rba_bal_file* f, double* cams, double* lms, int64_t* off, int32_t* oc, double* xy) {
+  if (!f) return RBA_ERR_INVALID_ARGUMENT;
+  if (cams) std::copy(f->p.cams.begin(), f->p.cams.end(), cams);
+  if (lms) std::copy(f->p.lms.begin(), f->p.lms.end(), lms);
+  if (off) std::copy(f->p.lm_off.begin(), f->p.lm_off.end(), off);
+  if (oc) std::copy(f->p.obs_cam.begin(), f->p.obs_cam.end(), oc);
+  if (xy) std::copy(f->p.obs_xy.begin(), f->p.obs_xy.end(), xy);
+  return RBA_OK;
+}
+int32_t rba_bal_load_timings(const rba_bal_file* f, double* out5) {
+  if (!f || !out5) return RBA_ERR_INVALID_ARGUMENT;
+  std::copy(f->timings, f->timings + 5, out5);
+  return RBA_OK;
+}
+int32_t rba_bal_free(rba_bal_file* f) { delete f; return RBA_OK; }
 
 int32_t rba_layout_selftest(const rba_problem_view* pv, int32_t rank, int32_t nranks, int32_t scalar_size) {
   using namespace rba;

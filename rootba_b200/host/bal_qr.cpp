@@ -1,6 +1,10 @@
 // bal_qr: square-root BA solver on a BAL file with the GPU linearizor (counterpart of src/app/bal_qr.cpp:44-115).
 //   bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI]
 //          [--residual-robust-norm NONE|HUBER] [--residual-huber-parameter X] [--no-normalize] [--dump-problem out.bin]
+//          [--loader parallel|map] [--num-threads T]
+//   --loader parallel (default): mmap + multi-threaded parse into flat arrays (bal_io_fast.hpp);
+//   --loader map: the reference-style fscanf + std::map loader (bal_problem.hpp).  Both give identical problems.
+#include <chrono>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -9,11 +13,30 @@
 
 using namespace rootba_b200;
 
+static double seconds_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+template <class S, class Problem>
+int solve_and_log(Problem& problem, const SolverOptions& o, const std::string& log_path);
+
 template <class S>
-int run(const std::string& input, bool normalize, const SolverOptions& o, const std::string& log_path) {
+int run(const std::string& input, bool normalize, const SolverOptions& o, const std::string& log_path, bool parallel_loader, int num_threads) {
+  const auto t0 = std::chrono::steady_clock::now();
+  if (parallel_loader) {
+    auto problem = load_normalized_bal_problem_parallel<S>(input, normalize, 100.0, num_threads);
+    std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s' in %.3fs (parallel loader)\n", problem.num_cameras(),
+                problem.num_landmarks(), (long long)problem.num_observations(), input.c_str(), seconds_since(t0));
+    return solve_and_log<S>(problem, o, log_path);
+  }
   auto problem = load_normalized_bal_problem<S>(input, normalize);
-  std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s'\n", problem.num_cameras(), problem.num_landmarks(),
-              (long long)problem.num_observations(), input.c_str());
+  std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s' in %.3fs (map loader)\n", problem.num_cameras(),
+              problem.num_landmarks(), (long long)problem.num_observations(), input.c_str(), seconds_since(t0));
+  return solve_and_log<S>(problem, o, log_path);
+}
+
+template <class S, class Problem>
+int solve_and_log(Problem& problem, const SolverOptions& o, const std::string& log_path) {
   SolverSummary summary;
   bundle_adjust_manual<S>(problem, o, &summary);
   std::ofstream f(log_path);  // minimal ba_log.json
@@ -34,7 +57,8 @@ int run(const std::string& input, bool normalize, const SolverOptions& o, const 
 
 int main(int argc, char** argv) {
   std::string input, dump, log_path = "ba_log.json";
-  bool use_double = true, normalize = true;
+  bool use_double = true, normalize = true, parallel_loader = true;
+  int num_threads = 0;
   SolverOptions o;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -52,6 +76,8 @@ int main(int argc, char** argv) {
     else if (a == "--residual-huber-parameter") o.huber_parameter = std::stod(next());
     else if (a == "--optimized-cost") { const std::string v = next(); o.optimized_cost = v == "ERROR" ? SolverOptions::OptimizedCost::ERROR : v == "ERROR_VALID" ? SolverOptions::OptimizedCost::ERROR_VALID : SolverOptions::OptimizedCost::ERROR_VALID_AVG; }
     else if (a == "--log-path") log_path = next();
+    else if (a == "--loader") { const std::string v = next(); if (v != "parallel" && v != "map") { std::cerr << "--loader parallel|map\n"; return 2; } parallel_loader = v == "parallel"; }
+    else if (a == "--num-threads") num_threads = std::stoi(next());
     else if (a == "--dump-problem") dump = next();
     else if (a == "--help" || a == "-h") { std::cout << "usage: bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI] ...\n"; return 0; }
     else { std::cerr << "unknown option " << a << "\n"; return 2; }
@@ -59,18 +85,27 @@ int main(int argc, char** argv) {
   if (input.empty()) { std::cerr << "--input is required\n"; return 2; }
   try {
     if (!dump.empty()) {  // loader check (host only, no GPU): normalised double arrays in SoA form
-      auto p = load_normalized_bal_problem<double>(input, normalize);
       std::vector<int64_t> off; std::vector<int32_t> oc; std::vector<double> xy, c, l;
-      p.export_topology(off, oc, xy); p.export_state(c, l);
+      int nc = 0, nl = 0;
+      const auto t0 = std::chrono::steady_clock::now();
+      if (parallel_loader) {
+        auto p = load_normalized_bal_problem_parallel<double>(input, normalize, 100.0, num_threads);
+        std::printf("load time %.3fs (parallel loader)\n", seconds_since(t0));
+        p.export_topology(off, oc, xy); p.export_state(c, l); nc = p.num_cameras(); nl = p.num_landmarks();
+      } else {
+        auto p = load_normalized_bal_problem<double>(input, normalize);
+        std::printf("load time %.3fs (map loader)\n", seconds_since(t0));
+        p.export_topology(off, oc, xy); p.export_state(c, l); nc = p.num_cameras(); nl = p.num_landmarks();
+      }
       std::ofstream f(dump, std::ios::binary);
-      const int64_t hdr[3] = {p.num_cameras(), p.num_landmarks(), (int64_t)oc.size()};
+      const int64_t hdr[3] = {nc, nl, (int64_t)oc.size()};
       f.write((const char*)hdr, sizeof(hdr));
       f.write((const char*)c.data(), c.size() * 8); f.write((const char*)l.data(), l.size() * 8);
       f.write((const char*)off.data(), off.size() * 8); f.write((const char*)oc.data(), oc.size() * 4); f.write((const char*)xy.data(), xy.size() * 8);
       return 0;
     }
     o.use_double = use_double;
-    return use_double ? run<double>(input, normalize, o, log_path) : run<float>(input, normalize, o, log_path);
+    return use_double ? run<double>(input, normalize, o, log_path, parallel_loader, num_threads) : run<float>(input, normalize, o, log_path, parallel_loader, num_threads);
   } catch (const std::exception& e) {
     std::cerr << "FATAL: " << e.what() << "\n";
     return 1;

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/rootba_b200.h"
+#include "bal_io_fast.hpp"
 #include "bal_problem.hpp"
 
 namespace rootba_b200 {
@@ -81,13 +82,15 @@ inline void check(int rc, bool allow_numerical_failure = false) {
   throw std::runtime_error(std::string("rootba_b200: ") + rba_last_error());  // the reference CHECK-aborts here
 }
 
-template <typename Scalar_>
+// Problem: BalProblem<Scalar> (reference-style AoS + std::map) or BalProblemSoA<Scalar> (flat, from the parallel loader)
+template <typename Scalar_, class Problem_ = BalProblem<Scalar_>>
 class LinearizorQR {
  public:
   using Scalar = Scalar_;
+  using Problem = Problem_;
   using VecX = std::vector<Scalar>;
 
-  static std::unique_ptr<LinearizorQR> create(BalProblem<Scalar>& bal_problem, const SolverOptions& options, SolverSummary* summary = nullptr) {
+  static std::unique_ptr<LinearizorQR> create(Problem& bal_problem, const SolverOptions& options, SolverSummary* summary = nullptr) {
     return std::unique_ptr<LinearizorQR>(new LinearizorQR(bal_problem, options, summary));
   }
   ~LinearizorQR() { if (h_) rba_destroy(h_); }
@@ -142,7 +145,7 @@ class LinearizorQR {
   rba_workload_stats stats() const { rba_workload_stats s; rba_get_workload_stats(h_, &s); return s; }
 
  private:
-  LinearizorQR(BalProblem<Scalar>& bp, const SolverOptions& o, SolverSummary* summary) : bal_problem_(bp), summary_(summary) {
+  LinearizorQR(Problem& bp, const SolverOptions& o, SolverSummary* summary) : bal_problem_(bp), summary_(summary) {
     rba_solver_opts so;
     rba_default_solver_opts(&so);
     so.use_householder_marginalization = o.use_householder_marginalization;
@@ -162,7 +165,7 @@ class LinearizorQR {
     bp.export_state(c, l);
     check(rba_set_state(h_, c.data(), l.data()));
   }
-  BalProblem<Scalar>& bal_problem_;
+  Problem& bal_problem_;
   SolverSummary* summary_ = nullptr;
   IterationSummary* it_summary_ = nullptr;
   rba_handle* h_ = nullptr;
@@ -172,15 +175,15 @@ class LinearizorQR {
 };
 
 // optimize_lm_ours (bal_bundle_adjustment.cpp:249-544): the host-serial LM loop, driving the GPU linearizor
-template <typename Scalar>
-void bundle_adjust_manual(BalProblem<Scalar>& bal_problem, const SolverOptions& o, SolverSummary* out = nullptr, bool quiet = false) {
+template <typename Scalar, class Problem>
+void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSummary* out = nullptr, bool quiet = false) {
   SolverSummary local;
   SolverSummary& summary = out ? *out : local;
   summary = SolverSummary();
   const Scalar min_lambda(1.0 / o.max_trust_region_radius), max_lambda(1.0 / o.min_trust_region_radius);
   const Scalar vee_factor(o.vee_factor), initial_vee(o.initial_vee);
   Scalar lambda(1.0 / o.initial_trust_region_radius), lambda_vee(initial_vee);
-  auto linearizor = LinearizorQR<Scalar>::create(bal_problem, o, &summary);
+  auto linearizor = LinearizorQR<Scalar, Problem>::create(bal_problem, o, &summary);
   auto cost_of = [&](const ResidualInfo& ri) {
     switch (o.optimized_cost) {
       case SolverOptions::OptimizedCost::ERROR: return ri.all.error;

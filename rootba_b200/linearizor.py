@@ -12,6 +12,7 @@ The optimisation state lives on the GPU; `BalProblem.cameras/landmarks` are refr
 from __future__ import annotations
 
 import ctypes as C
+import os
 import dataclasses
 import math
 
@@ -79,6 +80,27 @@ class BalProblem:
     @classmethod
     def from_arrays(cls, arrays, dtype=np.float64) -> "BalProblem":
         return cls(arrays.cams, arrays.lms, arrays.lm_off, arrays.obs_cam, arrays.obs_xy, dtype)
+
+    @classmethod
+    def load_bal(cls, path: str, dtype=np.float64, normalize: bool = True, scale: float = 100.0, num_threads: int = 0) -> "BalProblem":
+        """load_normalized_bal_problem (bal/bal_problem.cpp:773-852) through the library's multi-threaded BAL parser
+        (rba_bal_load): load + normalise in double, then cast to dtype."""
+        L = _lib.lib()
+        f = C.c_void_p()
+        check(L.rba_bal_load(os.fsencode(path), int(normalize), C.c_double(scale), int(num_threads), C.byref(f)))
+        try:
+            nc, nl, nobs = C.c_int32(), C.c_int32(), C.c_int64()
+            check(L.rba_bal_dims(f, C.byref(nc), C.byref(nl), C.byref(nobs)))
+            cams, lms = np.empty((nc.value, 10)), np.empty((nl.value, 3))
+            off, oc, xy = np.empty(nl.value + 1, np.int64), np.empty(nobs.value, np.int32), np.empty((nobs.value, 2))
+            check(L.rba_bal_copy(f, _p(cams), _p(lms), _p(off), _p(oc), _p(xy)))
+            t = (C.c_double * 5)()
+            check(L.rba_bal_load_timings(f, t))
+        finally:
+            L.rba_bal_free(f)
+        bp = cls(cams, lms, off, oc, xy, dtype)
+        bp.load_timings = dict(zip(("read", "count", "parse", "csr", "normalize"), t))
+        return bp
 
     def num_cameras(self): return self.cams.shape[0]
     def num_landmarks(self): return self.lms.shape[0]

@@ -53,12 +53,99 @@ def test_loader_matches_oracle_and_generator(tmp_path):
     assert rel_err(cams, ref["cams"]) < 1e-14 and rel_err(lms, ref["lms"]) < 1e-14 and np.array_equal(xy, ref["obs_xy"])
 
 
-def test_rejects_duplicate_observation(tmp_path):
+@pytest.mark.parametrize("loader", ["parallel", "map"])
+def test_rejects_duplicate_observation(tmp_path, loader):
     _build()
     p = tmp_path / "dup.txt"
     p.write_text("1 1 2\n0 0 1.0 2.0\n0 0 1.5 2.5\n" + "0\n" * 9 + "0\n0\n1\n")
-    r = subprocess.run([BAL_QR, "--input", str(p), "--dump-problem", str(tmp_path / "x.bin")], capture_output=True)
+    r = subprocess.run([BAL_QR, "--input", str(p), "--loader", loader, "--dump-problem", str(tmp_path / "x.bin")], capture_output=True)
     assert r.returncode != 0  # the reference CHECK-fails on a duplicate (cam, lm) pair (bal_problem.cpp:229-230)
+
+
+def _shuffled_bal_text(prob, seed, style):
+    """BAL text of `prob` with the observation lines in random order and mixed token separators / number styles:
+    the loaders tokenise on whitespace like fscanf, and must sort the observations of a landmark by camera."""
+    from scipy.spatial.transform import Rotation
+    from rootba_b200.synthetic import quat_to_rot
+    rng = np.random.default_rng(seed)
+    flip = np.diag([1.0, -1.0, -1.0])
+    rv = Rotation.from_matrix(np.einsum("ij,mjk->mik", flip, quat_to_rot(prob.cams[:, :4]))).as_rotvec()
+    tb = prob.cams[:, 4:7] @ flip.T
+    lm_of_obs = np.repeat(np.arange(prob.nl), np.diff(prob.lm_off))
+    fmt = {"g17": lambda v: f"{v:.17g}", "e6": lambda v: f"{v:.6e}", "plus": lambda v: f"{v:+.12e}"}[style]
+    sep = {"g17": " ", "e6": "\t", "plus": "  "}[style]
+    lines = [f"{prob.nc}{sep}{prob.nl}{sep}{prob.nobs}"]
+    for k in rng.permutation(prob.nobs):
+        x, y = prob.obs_xy[k]
+        lines.append(sep.join([str(prob.obs_cam[k]), str(lm_of_obs[k]), fmt(x), fmt(-y)]))
+    for i in range(prob.nc):
+        lines += [fmt(v) for v in (*rv[i], *tb[i], *prob.cams[i, 7:10])]
+    # landmark coordinates three per line: the format is token-based, not line-based
+    lines += [sep.join(fmt(v) for v in prob.lms[i]) for i in range(prob.nl)]
+    eol = "\r\n" if style == "e6" else "\n"
+    return eol.join(lines) + ("" if style == "plus" else eol)
+
+
+@pytest.mark.parametrize("style", ["g17", "e6", "plus"])
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_parallel_loader_is_bit_identical_to_map_loader(tmp_path, style, threads):
+    """the mmap + multi-threaded loader (bal_io_fast.hpp) and the reference-style fscanf + std::map loader
+    (bal_problem.hpp, after bal_problem.cpp:189-282) must produce the same bytes: topology, observations, state."""
+    from rootba_b200.synthetic import synth_bal
+    _build()
+    prob = synth_bal(23, 3000, 3.7, seed=17, normalize_scale=None)
+    path = tmp_path / "shuffled.txt"
+    path.write_text(_shuffled_bal_text(prob, seed=3, style=style))
+    dumps = {}
+    for loader in ("parallel", "map"):
+        out = str(tmp_path / f"{loader}.bin")
+        subprocess.check_call([BAL_QR, "--input", str(path), "--loader", loader, "--num-threads", str(threads), "--dump-problem", out],
+                              stdout=subprocess.DEVNULL)
+        dumps[loader] = open(out, "rb").read()
+    assert dumps["parallel"] == dumps["map"]
+    cams, lms, off, oc, xy = _read_dump(str(tmp_path / "parallel.bin"))
+    assert np.array_equal(off, prob.lm_off) and np.array_equal(oc, prob.obs_cam)  # sorted back: indexing bit-exact
+
+
+@pytest.mark.parametrize("text", [
+    "2 1 2\n0 0 1.0 2.0\n1 0 1.5 2.5\n" + "0\n" * 18 + "0\n0\n",          # file ends early
+    "2 1 2\n0 0 1.0 2.0\n2 0 1.5 2.5\n" + "0\n" * 18 + "0\n0\n1\n",       # camera index out of range
+    "2 1 2\n0 0 1.0 2.0\n1 0 1.5 abc\n" + "0\n" * 18 + "0\n0\n1\n",       # not a number
+    "0 1 2\n",                                                                 # bad header
+])
+def test_parallel_loader_rejects_malformed_files(tmp_path, text):
+    _build()
+    p = tmp_path / "bad.txt"
+    p.write_text(text)
+    r = subprocess.run([BAL_QR, "--input", str(p), "--loader", "parallel", "--dump-problem", str(tmp_path / "x.bin")], capture_output=True)
+    assert r.returncode != 0 and b"FATAL" in r.stderr
+
+
+def test_abi_loader_matches_map_loader_and_oracle(tmp_path):
+    """rba_bal_load (C ABI, used by BalProblem.load_bal) == bal_qr --loader map (bytes) == oracle loader (to rounding)"""
+    import rootba_b200 as rb
+    from oracle import oracle_py as orc
+    from rootba_b200.synthetic import synth_bal
+    _build()
+    prob = synth_bal(31, 2500, 4.2, seed=23, normalize_scale=None)
+    path = tmp_path / "p.txt"
+    path.write_text(_shuffled_bal_text(prob, seed=8, style="e6"))
+    for normalize in (False, True):
+        bp = rb.BalProblem.load_bal(str(path), np.float64, normalize=normalize, num_threads=4)
+        out = str(tmp_path / "map.bin")
+        subprocess.check_call([BAL_QR, "--input", str(path), "--loader", "map", "--dump-problem", out] + ([] if normalize else ["--no-normalize"]),
+                              stdout=subprocess.DEVNULL)
+        cams, lms, off, oc, xy = _read_dump(out)
+        assert np.array_equal(bp.lm_off, off) and np.array_equal(bp.obs_cam, oc)
+        assert np.array_equal(bp.obs_xy, xy) and np.array_equal(bp.cams, cams) and np.array_equal(bp.lms, lms)
+        ref = orc.load_bal(str(path), normalize=normalize)
+        assert np.array_equal(bp.lm_off, ref["lm_off"]) and np.array_equal(bp.obs_cam, ref["obs_cam"]) and np.array_equal(bp.obs_xy, ref["obs_xy"])
+        assert rel_err(bp.cams, ref["cams"]) < 1e-14 and rel_err(bp.lms, ref["lms"]) < 1e-14
+    assert set(bp.load_timings) == {"read", "count", "parse", "csr", "normalize"}
+    f32 = rb.BalProblem.load_bal(str(path), np.float32)
+    assert f32.cams.dtype == np.float32 and np.array_equal(f32.cams, bp.cams.astype(np.float32))  # cast after normalising (:813-832)
+    with pytest.raises(rb.RbaError):
+        rb.BalProblem.load_bal(str(tmp_path / "missing.txt"))
 
 
 @pytest.mark.gpu
