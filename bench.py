@@ -300,7 +300,8 @@ def bench_ours(args):
 
     def make_linearizor():
         bp = rb.BalProblem.from_arrays(arrays, dtype)
-        so = rb.SolverOptions(use_double=(dtype == np.float64), device=local_rank, rank=rank, nranks=world)
+        so = rb.SolverOptions(use_double=(dtype == np.float64), device=local_rank, rank=rank, nranks=world,
+                              operator_form=args.operator.upper())
         lin = rb.LinearizorQR.create(bp, so)
         if world > 1:
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -358,7 +359,11 @@ def bench_ours(args):
     stats = lin.stats()
     clocks = sampler.stop() if rank == 0 else {}
     mv_t = torch.tensor([mv_s], dtype=torch.float64, device="cuda")
-    mv_bytes = torch.tensor([float(stats["matvec_algorithmic_bytes"])], dtype=torch.float64, device="cuda")
+    sz = 4 if dtype == np.float32 else 8
+    dense_bytes = float(stats["matvec_algorithmic_bytes"])  # 18 M2 s + 18 Nobs s + 4 Nobs (dense Q2 panels)
+    # implicit form: jp (18) + q1d (27) records + x gather (9) + per-observation y written and read back (9 + 9), cam index
+    implicit_bytes = float(stats["num_observations_local"]) * (72 * sz + 4)
+    mv_bytes = torch.tensor([implicit_bytes if args.operator == "implicit" else dense_bytes], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(mv_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(mv_bytes, op=dist.ReduceOp.SUM)
@@ -366,7 +371,7 @@ def bench_ours(args):
     traffic = None
     try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same workload), per launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_matvec_traffic.json")))
-        if args.workload == "ladybug-1723" and args.scale == 1.0 and args.dtype == "f32" and world == 1:
+        if args.workload == "ladybug-1723" and args.scale == 1.0 and args.dtype == "f32" and world == 1 and args.operator == "dense":
             traffic = tj["traffic_bytes_per_launch"]
     except Exception:
         pass
@@ -413,12 +418,13 @@ def bench_ours(args):
             "data": "synthetic",
             "config": {"workload": f"synthetic {args.workload}" + (" (BAL ladybug problem-1723-156502 shape, BASELINE configs[1])" if args.workload == "ladybug-1723" else ""),
                        "scale": args.scale, "seed": args.seed, **full, "parallelism": f"landmark-shard x{world}",
-                       "solver": "SQUARE_ROOT/SCHUR_JACOBI/Householder, reference defaults",
+                       "solver": "SQUARE_ROOT/SCHUR_JACOBI/Householder, reference defaults" + (", operator_form=IMPLICIT (opt-in)" if args.operator == "implicit" else ""),
                        "l2": "inputs larger than L2 (Q2 panels %.0f MB vs 126 MB L2)" % (stats["panel_scalars"] * (4 if dtype == np.float32 else 8) / 1e6)},
             "e2e": {"value": e2e_ms, "unit": "ms/LM-iter", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", [])},
-            "roofline": {"bound": "hbm", "kernel": "rcs_matvec (k_matvec_small + k_cam_reduce)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "rcs_matvec (k_matvec_implicit + k_cam_reduce), bytes of the implicit form" if args.operator == "implicit"
+                         else "rcs_matvec (k_matvec_small + k_cam_reduce)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": float(mv_bytes.item()) / world, "us_per_launch": 1e6 * float(mv_t.item())},
             "cpu_baseline": cpu,
@@ -442,6 +448,8 @@ def main():
     ap.add_argument("--seed", type=int, default=38401)
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--operator", default="dense", choices=["dense", "implicit"],
+                    help="PCG operator form: dense = the reference's Q2-panel product (default, contract kernel); implicit = opt-in")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

@@ -76,7 +76,12 @@ typedef struct {
   int32_t nranks;                          /* 1 = single GPU */
   int32_t pcg_check_period;                /* host polls the device convergence flag every this many CG iterations (0 -> 4) */
   int32_t use_cuda_graphs;                 /* capture the CG iteration into CUDA graphs */
-  int32_t reserved[6];
+  int32_t operator_form;                   /* PCG operator (Q2^T Jp)^T (Q2^T Jp) x: 0 = dense Q2 panels, as the reference
+                                              (ipp:400-441; default, the contract kernel); 1 = implicit
+                                              Jp^T Jp x - (Q1d^T Jp)^T (Q1d^T Jp) x from the per-observation records
+                                              (same result up to rounding, ~n/2.7 x fewer bytes, but the subtraction gives
+                                              up the float32 robustness of the square-root form: recommended with f64) */
+  int32_t reserved[5];
 } rba_solver_opts;
 
 /* ResidualInfo (bal/residual_info.hpp:59-89) */

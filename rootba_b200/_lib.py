@@ -37,7 +37,7 @@ class SolverOpts(C.Structure):
                 ("max_linear_solver_iterations", C.c_int32), ("eta", C.c_double),
                 ("residual_reset_period", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32), ("pcg_check_period", C.c_int32), ("use_cuda_graphs", C.c_int32),
-                ("reserved", C.c_int32 * 6)]
+                ("operator_form", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class ResidualInfo(C.Structure):

@@ -1004,6 +1004,68 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
 }
 
 // ------------------------------------------------------------------------------------------------
+// K4i  the same operator in implicit form (opt-in: rba_solver_opts.operator_form = 1; SURVEY 8d last remark)
+//   [Q1d; P] is an orthogonal transform of [Jp; 0], so  P^T P = Jp^T Jp - Q1d^T Q1d  (the identity k_stage2 and
+//   k_precond_partial already use) and, per landmark with observations i,
+//       u   = sum_i Q1d_i x_i                      (3-vector;  x_i = the 9 entries of the camera of observation i)
+//       y_i = Jp_i^T (Jp_i x_i) - Q1d_i^T u
+//   The kernel reads the 80-byte jp and 112-byte q1d records (192 n bytes per landmark in f32) instead of the dense
+//   18 n^2 s panel.  It is the Schur-complement product in disguise: the subtraction cancels, so in float32 it gives up
+//   the numerical advantage that is the point of the square-root formulation -- hence opt-in, default stays the
+//   reference's dense Q2 panel product (ref: ipp:400-441).
+//   One warp per tile, one lane per observation (as k_stage2); writes yobs[slot][9], reduced per camera by
+//   k_cam_reduce_final over the observation CSR.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(128) k_matvec_implicit(DevPtrs<S> D, int tile_begin, const S* __restrict__ xvec, const int* done, int pdl) {
+  if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (done && *done) return;
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = tile_begin + blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+    const TileInfo T = D.tiles[t];
+    const int n = T.n, G = T.G;
+    const int g = lane / G, j = lane - g * G;
+    const bool active = g < T.nvalid;
+    const size_t sl0 = (size_t)(T.slot_base + g * n);
+    S u0 = 0, u1 = 0, u2 = 0;
+    if (active) {
+      for (int i = j; i < n; i += G) {
+        const size_t sl = sl0 + i;
+        S q[28];
+        load_rec<S, 28>(D.q1d + 28 * sl, q);
+        const S* xc = xvec + 9 * (size_t)D.slot_cam[sl];
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+          const S xv = xc[p];
+          u0 += q[p] * xv; u1 += q[9 + p] * xv; u2 += q[18 + p] * xv;
+        }
+      }
+    }
+    u0 = group_sum(u0, G); u1 = group_sum(u1, G); u2 = group_sum(u2, G);
+    if (active) {
+      for (int i = j; i < n; i += G) {
+        const size_t sl = sl0 + i;
+        S q[28], jp[20];
+        load_rec<S, 28>(D.q1d + 28 * sl, q);
+        load_rec<S, 20>(D.jp + 20 * sl, jp);
+        const S* xc = xvec + 9 * (size_t)D.slot_cam[sl];
+        S t0 = 0, t1 = 0;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+          const S xv = xc[p];
+          t0 += jp[p] * xv; t1 += jp[9 + p] * xv;
+        }
+        S* yo = D.yobs + 9 * sl;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) yo[p] = (jp[p] * t0 + jp[9 + p] * t1) - (q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K3a  block-Jacobi preconditioner blocks, camera-major (ref: ipp:520-552 SCHUR_JACOBI, :554-569 JACOBI)
 //   (Q2^T Jp)_i^T (Q2^T Jp)_i = Jp_i^T Jp_i - (Q1d^T Jp)_i^T (Q1d^T Jp)_i  (Q orthogonal, Givens on 6 rows)
 //   thread per ReduceItem chunk of <= 32 observations ... here: one thread per (item, 8-slot subchunk) would
@@ -1502,6 +1564,180 @@ __global__ void __launch_bounds__(WARPS * 32, RBA_K4_MINB) k_matvec_small_tma(De
       case 9: matvec_item_tma<S, 9, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
       default: break;
     }
+  }
+}
+
+// K4i, streamed: same arithmetic as k_matvec_implicit for the tiles [0, tile_end) whose W * n <= MAXSLOTS slots.
+// A tile's q1d and jp records are two contiguous chunks of HBM: lane 0 brings them into a per-warp 2-stage shared-memory
+// ring with two cp.async.bulk copies (mbarrier complete_tx), the next-but-one tile is requested as soon as a stage has
+// been consumed, and every lane then reads its own 112 / 80-byte records with 16-byte LDS (stride 28 words: conflict
+// free per quarter warp) instead of 12 uncoalesced 16-byte global loads per observation.  The per-observation results
+// leave through shared memory as one contiguous run per tile.  The records are constant during PCG, so the first two
+// tiles are requested before griddepcontrol.wait.
+template <class S>
+__device__ __forceinline__ void lds_rec28(const S* src, S (&v)[28]) {
+  if (sizeof(S) == 4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int q = 0; q < 7; ++q) { const float4 t = s4[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+  } else {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+    for (int q = 0; q < 14; ++q) { const double2 t = s2[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+  }
+}
+template <class S>
+__device__ __forceinline__ void lds_rec20(const S* src, S (&v)[20]) {
+  if (sizeof(S) == 4) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { const float4 t = s4[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+  } else {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) { const double2 t = s2[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+  }
+}
+
+// MAXSLOTS <= 64: a lane owns at most two observations (A: i = j, B: i = j + G).
+template <class S, int WARPS, int MAXSLOTS, int NS>
+__global__ void __launch_bounds__(WARPS * 32) k_matvec_implicit_tma(DevPtrs<S> D, int tile_end, const S* __restrict__ xvec,
+                                                                     const int* done, int pdl) {
+  static_assert(MAXSLOTS <= 64, "two observations per lane");
+  extern __shared__ __align__(128) unsigned char smem_imp[];
+  __shared__ __align__(8) uint64_t bars_all[WARPS][NS];
+  if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
+  constexpr int QBYTES = MAXSLOTS * 28 * (int)sizeof(S), JBYTES = MAXSLOTS * 20 * (int)sizeof(S);
+  constexpr int STAGE = QBYTES + JBYTES;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* base = smem_imp + (size_t)wib * NS * STAGE;
+  uint64_t* bars = bars_all[wib];
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  const uint64_t policy = l2_evict_first_policy();
+  const int stride = gridDim.x * WARPS;
+  const int first = blockIdx.x * WARPS + wib;
+  auto produce = [&](int t, int s) {
+    if (lane == 0) {
+      const TileInfo T = D.tiles[t];
+      const uint32_t wn = (uint32_t)((32 / T.G) * T.n);
+      const uint32_t qb = wn * 28u * (uint32_t)sizeof(S), jb = wn * 20u * (uint32_t)sizeof(S);
+      mbar_expect_tx(&bars[s], qb + jb);
+      bulk_g2s(base + (size_t)s * STAGE, D.q1d + 28 * (size_t)T.slot_base, qb, &bars[s], policy);
+      bulk_g2s(base + (size_t)s * STAGE + QBYTES, D.jp + 20 * (size_t)T.slot_base, jb, &bars[s], policy);
+    }
+  };
+  // the records are constant during PCG: request the first NS tiles before the grid dependency is awaited
+  int issued = 0;
+  for (int t = first; t < tile_end && issued < NS; t += stride) produce(t, issued++);
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (done && *done) {
+    for (int s = 0; s < issued; ++s) mbar_wait(&bars[s], 0);  // drain the copies in flight before the CTA may exit
+    return;
+  }
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // x of the two observations of a lane is gathered one tile ahead (index loads at the top of the previous iteration,
+  // value loads after its first pass), so the dependent slot_cam -> x round trips overlap compute
+  S x0[9], x1[9];
+  int cn0 = 0, cn1 = 0;
+  bool hn0 = false, hn1 = false;
+  TileInfo Tn = D.tiles[min(first, tile_end - 1)];
+  auto next_indices = [&](const TileInfo& T2, bool valid) {
+    const int g2 = lane / T2.G, j2 = lane - g2 * T2.G;
+    const bool act = valid && g2 < T2.nvalid;
+    hn0 = act && j2 < T2.n; hn1 = act && j2 + T2.G < T2.n;
+    cn0 = hn0 ? __ldg(D.slot_cam + T2.slot_base + g2 * T2.n + j2) : 0;
+    cn1 = hn1 ? __ldg(D.slot_cam + T2.slot_base + g2 * T2.n + j2 + T2.G) : 0;
+  };
+  auto next_values = [&]() {
+#pragma unroll
+    for (int p = 0; p < 9; ++p) {
+      x0[p] = hn0 ? __ldg(xvec + 9 * (size_t)cn0 + p) : S(0);
+      x1[p] = hn1 ? __ldg(xvec + 9 * (size_t)cn1 + p) : S(0);
+    }
+  };
+  next_indices(Tn, first < tile_end);
+  next_values();
+  int k = 0;
+  for (int t = first; t < tile_end; t += stride, ++k) {
+    const int s = k % NS;
+    const TileInfo T = Tn;
+    const int n = T.n, G = T.G;
+    const int g = lane / G, j = lane - g * G;
+    const bool hasA = hn0, hasB = hn1;
+    const int eA = g * n + j, eB = eA + G;
+    S xa[9], xb[9];
+#pragma unroll
+    for (int p = 0; p < 9; ++p) { xa[p] = x0[p]; xb[p] = x1[p]; }
+    const bool more = t + stride < tile_end;
+    if (more) Tn = D.tiles[t + stride];
+    next_indices(Tn, more);
+    mbar_wait(&bars[s], (uint32_t)((k / NS) & 1));
+    S* sq = reinterpret_cast<S*>(base + (size_t)s * STAGE);
+    const S* sj = reinterpret_cast<const S*>(base + (size_t)s * STAGE + QBYTES);
+    // ---- pass 1: u = sum_i Q1d_i x_i over the landmark ----
+    S u0 = 0, u1 = 0, u2 = 0;
+    {
+      S q[28];
+      if (hasA) {
+        lds_rec28<S>(sq + 28 * eA, q);
+#pragma unroll
+        for (int p = 0; p < 9; ++p) { u0 += q[p] * xa[p]; u1 += q[9 + p] * xa[p]; u2 += q[18 + p] * xa[p]; }
+      }
+      if (hasB) {
+        lds_rec28<S>(sq + 28 * eB, q);
+#pragma unroll
+        for (int p = 0; p < 9; ++p) { u0 += q[p] * xb[p]; u1 += q[9 + p] * xb[p]; u2 += q[18 + p] * xb[p]; }
+      }
+    }
+    u0 = group_sum_p(u0, G); u1 = group_sum_p(u1, G); u2 = group_sum_p(u2, G);
+    next_values();  // the index loads issued at the top have landed by now
+    // ---- pass 2: y_i = Jp_i^T (Jp_i x_i) - Q1d_i^T u, kept in registers until every lane is done with the records ----
+    S ya[9], yb[9];
+    {
+      S q[28], jp[20];
+      if (hasA) {
+        lds_rec28<S>(sq + 28 * eA, q);
+        lds_rec20<S>(sj + 20 * eA, jp);
+        S t0 = 0, t1 = 0;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) { t0 += jp[p] * xa[p]; t1 += jp[9 + p] * xa[p]; }
+#pragma unroll
+        for (int p = 0; p < 9; ++p) ya[p] = (jp[p] * t0 + jp[9 + p] * t1) - (q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2);
+      }
+      if (hasB) {
+        lds_rec28<S>(sq + 28 * eB, q);
+        lds_rec20<S>(sj + 20 * eB, jp);
+        S t0 = 0, t1 = 0;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) { t0 += jp[p] * xb[p]; t1 += jp[9 + p] * xb[p]; }
+#pragma unroll
+        for (int p = 0; p < 9; ++p) yb[p] = (jp[p] * t0 + jp[9 + p] * t1) - (q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2);
+      }
+    }
+    __syncwarp();
+    // the q1d records of this stage are dead: reuse their space to turn the per-lane results into one contiguous run
+    if (hasA) {
+#pragma unroll
+      for (int p = 0; p < 9; ++p) sq[9 * eA + p] = ya[p];
+    }
+    if (hasB) {
+#pragma unroll
+      for (int p = 0; p < 9; ++p) sq[9 * eB + p] = yb[p];
+    }
+    __syncwarp();
+    {
+      const int cnt = T.nvalid * n * 9;
+      S* yg = D.yobs + 9 * (size_t)T.slot_base;
+      for (int e = lane; e < cnt; e += 32) yg[e] = sq[e];
+    }
+    __syncwarp();
+    // this stage is free again: request the tile NS steps ahead into it
+    if (t + NS * stride < tile_end) produce(t + NS * stride, s);
   }
 }
 

@@ -69,6 +69,10 @@ struct rba_handle {
   virtual int ipc_import(const void* all) = 0;
 };
 
+#ifndef RBA_IMP_NS
+#define RBA_IMP_NS 1
+#endif
+
 namespace rba {
 
 template <class S>
@@ -89,6 +93,12 @@ struct Solver : rba_handle {
   int* d_csr_obs_slots = nullptr; ReduceItem* d_csr_obs_items = nullptr; int* d_csr_obs_item_ptr = nullptr;
   int* d_csr_y_slots = nullptr; ReduceItem* d_csr_y_items = nullptr; int* d_csr_y_item_ptr = nullptr;
   int n_obs_items = 0, n_y_items = 0;
+  // camera-major CSR the operator's per-slot output is reduced over: the y-slot CSR of the dense form (one slot per
+  // observation and row chunk) or the observation CSR of the implicit form
+  const int* op_slots = nullptr; const ReduceItem* op_items = nullptr; const int* op_item_ptr = nullptr; int n_op_items = 0;
+  bool implicit_op = false;
+  int imp_tile_split = 0;        // tiles [0, split) have <= IMP_MAXSLOTS slots and take the streamed kernel
+  size_t imp_smem = 0; int imp_grid = 1;
   ReduceItem* d_pb_items = nullptr; int* d_pb_item_ptr = nullptr; int n_pb_items = 0;
   double* d_part = nullptr;      // [NPART][3]
   double* d_part_pq = nullptr;   // [NPART]
@@ -226,6 +236,18 @@ struct Solver : rba_handle {
       TRY(upload(&d_csr_y_item_ptr, L.csr_y.cam_item_ptr));
       n_y_items = (int)L.csr_y.items.size();
     }
+    implicit_op = opt.operator_form == 1;
+    if (opt.operator_form != 0 && opt.operator_form != 1) { g_err = "operator_form must be 0 (dense) or 1 (implicit)"; return RBA_ERR_INVALID_ARGUMENT; }
+    if (implicit_op) {
+      while (imp_tile_split < (int)L.tiles.size() && (32 / L.tiles[imp_tile_split].G) * L.tiles[imp_tile_split].n <= IMP_MAXSLOTS) ++imp_tile_split;
+      imp_smem = (size_t)IMP_WARPS * IMP_NS * (size_t)IMP_MAXSLOTS * 48 * sizeof(S);
+      CU(cudaFuncSetAttribute((k_matvec_implicit_tma<S, IMP_WARPS, IMP_MAXSLOTS, IMP_NS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)imp_smem));
+      int bps = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (k_matvec_implicit_tma<S, IMP_WARPS, IMP_MAXSLOTS, IMP_NS>), IMP_WARPS * 32, imp_smem));
+      imp_grid = std::max(1, std::min((imp_tile_split + IMP_WARPS - 1) / IMP_WARPS, sm_count * std::max(1, bps)));
+    }
+    if (implicit_op) { op_slots = d_csr_obs_slots; op_items = d_csr_obs_items; op_item_ptr = d_csr_obs_item_ptr; n_op_items = n_obs_items; }
+    else { op_slots = d_csr_y_slots; op_items = d_csr_y_items; op_item_ptr = d_csr_y_item_ptr; n_op_items = n_y_items; }
     TRY(upload(&d_pb_items, L.pb_items));
     TRY(upload(&d_pb_item_ptr, L.pb_cam_item_ptr));
     n_pb_items = (int)L.pb_items.size();
@@ -321,6 +343,7 @@ struct Solver : rba_handle {
     return RBA_OK;
   }
   static constexpr int K4_WARPS = 4;
+  static constexpr int IMP_WARPS = 2, IMP_MAXSLOTS = 64, IMP_NS = RBA_IMP_NS;  // streamed implicit operator: warps per block, slots per stage, stages per warp
 #ifndef RBA_K4_NS
 #define RBA_K4_NS 2
 #endif
@@ -522,10 +545,21 @@ struct Solver : rba_handle {
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
   void matvec_launch(const S* xvec, const int* done) {
     matvec_kernels(xvec, done);
-    k_cam_reduce<S><<<grid_for(n_y_items, 8, 8), 256, 0, stream>>>(D.yobs, d_csr_y_slots, d_csr_y_items, n_y_items, D.partial, done);
+    k_cam_reduce<S><<<grid_for(n_op_items, 8, 8), 256, 0, stream>>>(D.yobs, op_slots, op_items, n_op_items, D.partial, done);
     ++launches;
   }
   void matvec_kernels(const S* xvec, const int* done, bool pdl = false) {
+    if (implicit_op) {
+      const int ntl = (int)L.tiles.size();
+      const bool p = pdl && use_pdl && imp_tile_split == ntl;  // a single kernel between the PCG vector step and the reduction
+      if (imp_tile_split > 0 && use_tma)
+        launch_ex((k_matvec_implicit_tma<S, IMP_WARPS, IMP_MAXSLOTS, IMP_NS>), imp_grid, IMP_WARPS * 32, imp_smem, p, 1, D, imp_tile_split, xvec, done, (int)p);
+      const int tb = use_tma ? imp_tile_split : 0;
+      if (tb < ntl)
+        launch_ex(k_matvec_implicit<S>, (ntl - tb + TILE_WARPS - 1) / TILE_WARPS, TILE_WARPS * 32, 0, false, 1, D, tb, xvec, done, 0);
+      ++tm.matvec_launches;
+      return;
+    }
     const int nitems = (int)L.items.size();
     if (L.n_items_large > 0) {
       k_matvec_large<S, K4_WARPS, KPMAX><<<grid_for(L.n_items_large, K4_WARPS, 4), K4_WARPS * 32, k4_smem_small, stream>>>(
@@ -556,8 +590,8 @@ struct Solver : rba_handle {
     const bool fused = opt.nranks > 1 && peer_ok;
     if (fused) ++ar_seq;
     S* ydst = fused ? ybuf + (size_t)(ar_seq & 1) * 9 * nc : D.y;
-    int rc = launch_ex(k_cam_reduce_final<S>, grid_for(n_y_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, (const int*)d_csr_y_slots,
-                       (const ReduceItem*)d_csr_y_items, n_y_items, (const int*)d_csr_y_item_ptr, D.partial, d_cam_cnt, ydst, (const int*)&d_state->done, (int)use_pdl);
+    int rc = launch_ex(k_cam_reduce_final<S>, grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
+                       op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, ydst, (const int*)&d_state->done, (int)use_pdl);
     if (rc) return rc;
     if (opt.nranks == 1) return pcg_vec(i, mode, true, is_last, lambda);
     if (fused) return pcg_vec(i, mode, true, is_last, lambda, true);
@@ -567,10 +601,10 @@ struct Solver : rba_handle {
   // q_out = H vec = sum + lambda vec ; optional partial p.q
   int matvec_finish(const S* vec, S* out, S lambda, PcgState* st, double* part) {
     if (opt.nranks == 1) {
-      k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, D.partial, d_csr_y_item_ptr, nullptr, vec, out, lambda, part);
+      k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, D.partial, op_item_ptr, nullptr, vec, out, lambda, part);
       ++launches;
     } else {
-      k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, d_csr_y_item_ptr, nc, D.y, st ? &st->done : nullptr);
+      k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, op_item_ptr, nc, D.y, st ? &st->done : nullptr);
       int rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
       k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, nullptr, nullptr, D.y, vec, out, lambda, part);
       launches += 2;

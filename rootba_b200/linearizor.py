@@ -56,6 +56,7 @@ class SolverOptions:  # bal/solver_options.hpp (QR-relevant subset, reference de
     rank: int = 0
     nranks: int = 1
     pcg_check_period: int = 4
+    operator_form: str = "DENSE"                  # DENSE (reference: Q2 panels) | IMPLICIT (Jp^T Jp - Q1d^T Q1d from records)
 
     def use_projection_validity_check(self) -> bool:  # solver_options.cpp:41-51
         return self.optimized_cost != "ERROR"
@@ -155,6 +156,7 @@ class LinearizorQR:
         o.eta = options.eta
         o.device, o.rank, o.nranks = options.device, options.rank, options.nranks
         o.pcg_check_period = options.pcg_check_period
+        o.operator_form = {"DENSE": 0, "IMPLICIT": 1}[options.operator_form]
         self._opts = o
         pv = ProblemView(bal_problem.num_cameras(), bal_problem.num_landmarks(), bal_problem.num_observations(),
                          bal_problem.lm_off.ctypes.data, bal_problem.obs_cam.ctypes.data, bal_problem.obs_xy.ctypes.data)

@@ -36,6 +36,8 @@ def make_pair(arrays, dtype, **opt_kw):
     if "use_householder_marginalization" in opt_kw:
         so.use_householder_marginalization = bool(opt_kw["use_householder_marginalization"])
         okw["use_householder"] = int(so.use_householder_marginalization)
+    if "operator_form" in opt_kw:
+        so.operator_form = opt_kw["operator_form"]  # device-side choice only: the oracle always does the dense product
     if "max_num_iterations" in opt_kw:
         so.max_num_iterations = okw["max_num_iterations"] = opt_kw["max_num_iterations"]
     bp = rb.BalProblem.from_arrays(arrays, dtype)
@@ -161,6 +163,7 @@ def test_backup_restore(small_problem):
     (np.float32, {"robust_norm": "HUBER", "huber_parameter": 2.0}),
     (np.float64, {"optimized_cost": "ERROR_VALID"}),
     (np.float64, {"use_householder_marginalization": False}),
+    (np.float64, {"operator_form": "IMPLICIT"}),
 ])
 def test_lm_trajectory(small_problem, dtype, kw):
     import rootba_b200 as rb
@@ -196,6 +199,29 @@ def test_lm_trajectory(small_problem, dtype, kw):
         prev = b["cost"]
     assert g_it[-1]["cost"]["all"]["error"] < 0.2 * g_it[0]["cost"]["all"]["error"]
     assert abs(g_it[-1]["cost"]["all"]["error"] - rows[-1]["cost"]) <= max(tol, 1e-6) * rows[-1]["cost"]
+    lin.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("which", ["small", "mixed"])
+def test_implicit_operator_form(small_problem, mixed_problem, dtype, which):
+    """operator_form=IMPLICIT (Jp^T Jp x - Q1d^T Q1d x from the per-observation records) against the oracle's dense
+    Q2-panel product (ipp:400-441).  f64 at the single-stage tolerance; f32 one decade looser: the implicit form
+    subtracts two nearly equal positive terms."""
+    arrays = small_problem if which == "small" else mixed_problem
+    bp, lin, o, _ = make_pair(arrays, dtype, operator_form="IMPLICIT")
+    tol = TOL1[dtype] * (10 if dtype == np.float32 else 1)
+    lin.linearize(); assert o.linearize()
+    for lam in (0.1, 1e-4):
+        inc_g = lin.solve(lam)
+        inc_c, dbg = o.solve(lam, want_debug=True)
+        x = np.random.default_rng(7).uniform(-1, 1, 9 * lin.nc).astype(dtype)
+        assert rel_err(lin.right_multiply(x), o.right_multiply(x)) < tol * 4
+        assert lin.last_cg.termination_type == dbg["cg_termination"]
+        assert abs(lin.last_cg.num_iterations - dbg["cg_iterations"]) <= (2 if dtype == np.float64 else max(2, int(0.3 * dbg["cg_iterations"])))
+        assert rel_err(inc_g, inc_c) < TOLS[dtype] * (5 if dtype == np.float32 else 1)
+    l_g, l_c = lin.apply(inc_g), o.apply(inc_c)
+    assert abs(l_g - l_c) <= 50 * TOLS[dtype] * abs(l_c)
     lin.close()
 
 
