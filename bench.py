@@ -229,8 +229,21 @@ def hbm_peak():
 
 
 def make_problem(args):
-    from rootba_b200.synthetic import synth_config
-    return synth_config(args.workload, seed=args.seed, scale=args.scale)
+    """the synthetic stand-in; with RBA_BENCH_CACHE_DIR set the generated arrays are kept there (npz) so that several
+    bench invocations on one box (dense / implicit, the ranks of one torchrun) generate a large problem only once"""
+    from rootba_b200.synthetic import BalArrays, synth_config
+    cache = os.environ.get("RBA_BENCH_CACHE_DIR")
+    path = os.path.join(cache, f"{args.workload}_s{args.seed}_x{args.scale}.npz") if cache else None
+    if path and os.path.exists(path):
+        z = np.load(path)
+        return BalArrays(z["cams"], z["lms"], z["lm_off"], z["obs_cam"], z["obs_xy"])
+    arrays = synth_config(args.workload, seed=args.seed, scale=args.scale)
+    if path:
+        os.makedirs(cache, exist_ok=True)
+        tmp = f"{path}.{os.getpid()}.tmp.npz"
+        np.savez(tmp, cams=arrays.cams, lms=arrays.lms, lm_off=arrays.lm_off, obs_cam=arrays.obs_cam, obs_xy=arrays.obs_xy)
+        os.replace(tmp, path)
+    return arrays
 
 
 def run_lm(backend, dtype, warmup, steps, timer=None, barrier=None):

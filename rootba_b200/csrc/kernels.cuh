@@ -41,6 +41,7 @@ struct KOpts {
   int robust_norm;
   double huber;
   double jacobi_eps;  // effective epsilon (already resolved)
+  int write_panel;    // 0 with operator_form = implicit: the dense Q2 panels are neither stored nor read
 };
 
 // PCG scalars live on the device in double (ref: cg/conjugate_gradient.hpp:124-263 keeps them in double)
@@ -802,7 +803,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
             rot_apply(g2, f[v], y);
             cur2[v] = y;
           }
-          if (active) pk[(size_t)(t + 2 - 3) * KP * 32] = mk2(vc[0] ? f[0] : S(0), vc[1] ? f[1] : S(0));
+          if (active && o.write_panel) pk[(size_t)(t + 2 - 3) * KP * 32] = mk2(vc[0] ? f[0] : S(0), vc[1] ? f[1] : S(0));
         }
 #pragma unroll
         for (int v = 0; v < 2; ++v)
@@ -846,7 +847,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
         }
       }
       // rows 3..2n-1 = Q2^T Jp: out = -V[r] . w ; the two rows that carry the original Jacobian entries are patched below
-      if (active) {
+      if (active && o.write_panel) {
         V2* pk = ptile + (size_t)k * 32 + lane;
         const S nw00 = vc[0] ? -w0[0] : S(0), nw01 = vc[0] ? -w1[0] : S(0), nw02 = vc[0] ? -w2[0] : S(0);
         const S nw10 = vc[1] ? -w0[1] : S(0), nw11 = vc[1] ? -w1[1] : S(0), nw12 = vc[1] ? -w2[1] : S(0);
@@ -900,7 +901,7 @@ __host__ __device__ inline int stage2_need(int n, int G, int KP) {
 // 16-byte vector accesses straight from / to registers; only the 3 damping rows (which must land in the
 // column-interleaved panel layout) and the gradient are staged through shared memory for coalesced stores.
 template <class S>
-__global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<S> sc) {
+__global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<S> sc, int write_panel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using V2 = typename ST<S>::V2;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -987,7 +988,7 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
     {
       const int nsl = T.nvalid * n;
       for (int e = lane; e < nsl * 9; e += 32) D.yobs[9 * (size_t)T.slot_base + e] = sG[e];
-      if (active) {
+      if (active && write_panel) {
         V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off) + (size_t)(2 * n - 3) * KP * 32 + lane;
         for (int k = 0; k < KP; ++k) {
           const int c = 2 * j + 2 * G * k;

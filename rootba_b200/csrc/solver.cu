@@ -205,6 +205,7 @@ struct Solver : rba_handle {
     nl_total = pv->num_landmarks;
     ko.use_valid_projections_only = opt.use_valid_projections_only;
     ko.robust_norm = opt.robust_norm;
+    ko.write_panel = opt.operator_form == 1 ? 0 : 1;
     ko.huber = opt.huber_parameter;
     ko.jacobi_eps = opt.jacobi_scaling_epsilon > 0 ? opt.jacobi_scaling_epsilon : (double)ST<S>::eps_sqrt();  // ref: linearizor_base.cpp:72-79
     std::string msg = build_layout(nc, nl_total, pv->lm_obs_offset, pv->obs_cam_idx, opt.rank, opt.nranks, KPMAX, L);
@@ -255,7 +256,7 @@ struct Solver : rba_handle {
     D.slot_cam = d_slot_cam; D.slot_lm = d_slot_lm; D.slot_xy = d_xy; D.nslots = L.nslots; D.nc = nc;
     TRY(dalloc(&D.cams, (size_t)10 * nc)); TRY(dalloc(&cams_bk, (size_t)10 * nc));
     TRY(dalloc(&D.lms, (size_t)3 * L.nl_local)); TRY(dalloc(&lms_bk, (size_t)3 * L.nl_local));
-    TRY(dalloc(&D.panel, (size_t)L.panel_scalars));
+    if (opt.operator_form != 1) TRY(dalloc(&D.panel, (size_t)L.panel_scalars));  // the implicit operator never touches the panels
     TRY(dalloc(&D.jp, (size_t)20 * L.nslots));
     TRY(dalloc(&D.q1u, (size_t)28 * L.nslots));
     TRY(dalloc(&D.q1d, (size_t)28 * L.nslots));
@@ -620,7 +621,7 @@ struct Solver : rba_handle {
     tm.matvec_launches = 0;
     int rc = start(ev_stage2); if (rc) return rc;
     // stage 2: landmark damping + gradient (+ SCHUR_JACOBI blocks)
-    k_stage2<S><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc);
+    k_stage2<S><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc, ko.write_panel);
     ++launches;
     rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b, nullptr); if (rc) return rc;
     const bool schur = opt.preconditioner_type == 1;
@@ -803,6 +804,7 @@ struct Solver : rba_handle {
     const int n = T.n, G = T.G, KP = T.KP, g = sidx - T.lm_base;
     const int pad = (4 - (9 * n) % 4) % 4, lm_idx = 9 * n + pad, res_idx = lm_idx + 3;
     if (rows != 2 * n + 3 || cols != res_idx + 1) { g_err = "block dims mismatch"; return RBA_ERR_INVALID_ARGUMENT; }
+    if (!D.panel) { g_err = "rba_debug_get_block needs operator_form = 0 (no Q2 panels are stored for the implicit operator)"; return RBA_ERR_UNSUPPORTED; }
     CU(cudaStreamSynchronize(stream));
     std::vector<S> panel((size_t)2 * n * KP * 64), rec((size_t)28 * n), lmk(24);
     const int slot0 = T.slot_base + g * n;

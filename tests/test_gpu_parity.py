@@ -222,6 +222,12 @@ def test_implicit_operator_form(small_problem, mixed_problem, dtype, which):
         assert rel_err(inc_g, inc_c) < TOLS[dtype] * (5 if dtype == np.float32 else 1)
     l_g, l_c = lin.apply(inc_g), o.apply(inc_c)
     assert abs(l_g - l_c) <= 50 * TOLS[dtype] * abs(l_c)
+    import rootba_b200 as rb
+    with pytest.raises(rb.RbaError):  # no Q2 panels are stored in this mode
+        lin.debug_get_block(0)
+    dense = rb.LinearizorQR.create(rb.BalProblem.from_arrays(arrays, dtype), rb.SolverOptions())
+    assert lin.stats()["device_bytes"] < dense.stats()["device_bytes"]
+    dense.close()
     lin.close()
 
 
