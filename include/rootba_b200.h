@@ -231,7 +231,8 @@ int32_t rba_back_substitute_f64(rba_handle* h, const double* pose_inc, double* l
 /* One landmark block in the reference's storage layout, rows x cols row-major with
  * cols = 9n + pad + 4 (landmark_block_dynamic.hpp:56-66): rows 0..2 = Q1^T[Jp|Jl|r] (damped if damping is
  * active), rows 3..2n-1 = Q2^T Jp (Jl and r columns of these rows are reported as 0 / not stored),
- * rows 2n..2n+2 = damping rows.  `lm` is the landmark index in problem order (must be in this shard). */
+ * rows 2n..2n+2 = damping rows.  `lm` is the landmark index in problem order (must be in this shard).
+ * RBA_ERR_UNSUPPORTED with operator_form = 1 (no Q2 panels exist in that mode). */
 int32_t rba_debug_get_block(rba_handle* h, int32_t lm, void* out, int32_t rows, int32_t cols,
                             void* jl_col_scale3_out);
 
