@@ -21,6 +21,8 @@
 //       (src/rootba/qr/linearization_qr.test.cpp:120-222)
 //   - implicit matvec vs explicit sparse Q2^T Jp
 //       (src/rootba/qr/linearization_qr.test.cpp:63-110)
+// and by an independent dense float64 numpy derivation of the whole LM inner step
+// from the per-observation Jacobians (tests/test_oracle_dense_numpy.py).
 // Third-party arithmetic restated from its published behaviour:
 //   Eigen 3.4.0 (makeHouseholder / applyHouseholderOnTheLeft / JacobiRotation /
 //   LLT), Sophus@d0b7315a (SO3::exp, SE3), basalt-headers@91293fa4
