@@ -9,6 +9,7 @@
 #include <fstream>
 #include <iostream>
 
+#include "ba_log.hpp"
 #include "solver.hpp"
 
 using namespace rootba_b200;
@@ -18,7 +19,7 @@ static double seconds_since(std::chrono::steady_clock::time_point t0) {
 }
 
 template <class S, class Problem>
-int solve_and_log(Problem& problem, const SolverOptions& o, const std::string& log_path);
+int solve_and_log(Problem& problem, const SolverOptions& o, const std::string& log_path, const std::string& input, double load_time);
 
 template <class S>
 int run(const std::string& input, bool normalize, const SolverOptions& o, const std::string& log_path, bool parallel_loader, int num_threads) {
@@ -27,32 +28,61 @@ int run(const std::string& input, bool normalize, const SolverOptions& o, const 
     auto problem = load_normalized_bal_problem_parallel<S>(input, normalize, 100.0, num_threads);
     std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s' in %.3fs (parallel loader)\n", problem.num_cameras(),
                 problem.num_landmarks(), (long long)problem.num_observations(), input.c_str(), seconds_since(t0));
-    return solve_and_log<S>(problem, o, log_path);
+    return solve_and_log<S>(problem, o, log_path, input, seconds_since(t0));
   }
   auto problem = load_normalized_bal_problem<S>(input, normalize);
   std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s' in %.3fs (map loader)\n", problem.num_cameras(),
               problem.num_landmarks(), (long long)problem.num_observations(), input.c_str(), seconds_since(t0));
-  return solve_and_log<S>(problem, o, log_path);
+  return solve_and_log<S>(problem, o, log_path, input, seconds_since(t0));
 }
 
 template <class S, class Problem>
-int solve_and_log(Problem& problem, const SolverOptions& o, const std::string& log_path) {
+int solve_and_log(Problem& problem, const SolverOptions& o, const std::string& log_path, const std::string& input, double load_time) {
+  const DatasetSummary ds = summarize_problem<S>(problem, input);
   SolverSummary summary;
   bundle_adjust_manual<S>(problem, o, &summary);
-  std::ofstream f(log_path);  // minimal ba_log.json
-  f.precision(17);  // (bal/ba_log.hpp:139-237: per-iteration costs and timings)
-  f << "{\n  \"_solver_summary\": {\"solver_type\": \"bal_qr_b200\", \"termination_type\": \"" << summary.termination_type << "\", \"message\": \""
-    << summary.message << "\"},\n  \"_iterations\": [\n";
-  for (size_t i = 0; i < summary.iterations.size(); ++i) {
-    const auto& it = summary.iterations[i];
-    f << "    {\"iteration\": " << it.iteration << ", \"cost\": " << it.cost.all.error << ", \"cost_valid\": " << it.cost.valid.error
-      << ", \"step_is_successful\": " << (it.step_is_successful ? "true" : "false") << ", \"linear_solver_iterations\": " << it.linear_solver_iterations
-      << ", \"stage1_time_in_seconds\": " << it.stage1_time_in_seconds << ", \"stage2_time_in_seconds\": " << it.stage2_time_in_seconds
-      << ", \"solve_reduced_system_time_in_seconds\": " << it.solve_reduced_system_time_in_seconds
-      << ", \"back_substitution_time_in_seconds\": " << it.back_substitution_time_in_seconds << "}" << (i + 1 < summary.iterations.size() ? "," : "") << "\n";
-  }
-  f << "  ]\n}\n";
+  PipelineTimingSummary pt;
+  pt.load_time = load_time;
+  pt.optimize_time = summary.total_time_in_seconds;
+  // ba_log.json in the reference's format (bal/ba_log.hpp:139-252, ba_log.cpp:62-150), see ba_log.hpp
+  if (!write_ba_log(log_path, ds, pt, summary)) { std::cerr << "Could not save BA log to " << log_path << "\n"; return 1; }
   return 0;
+}
+
+// --selftest-log: the log writer on a fabricated 4-iteration summary (accepted, rejected, accepted) -- no GPU needed
+static int selftest_log(const std::string& path) {
+  SolverSummary s;
+  s.termination_type = "CONVERGENCE";
+  s.message = "Function tolerance reached.";
+  const double costs[4] = {100.0, 40.0, 55.0, 39.99999};
+  const bool ok[4] = {true, true, false, true};
+  for (int i = 0; i < 4; ++i) {
+    IterationSummary it;
+    it.iteration = i;
+    it.cost.all = {10, costs[i], 10 * std::sqrt(costs[i])};
+    it.cost.valid = {9, 0.9 * costs[i], 9 * std::sqrt(costs[i])};
+    it.step_is_valid = true;
+    it.step_is_successful = ok[i];
+    it.trust_region_radius = 1e4 * (i + 1);
+    it.relative_decrease = i ? 0.5 : 0.0;
+    it.linear_solver_iterations = 3 * i;
+    it.stage1_time_in_seconds = i ? 0.001 : 0.0;
+    it.stage2_time_in_seconds = 0.002 * i;
+    it.solve_reduced_system_time_in_seconds = 0.01 * i;
+    it.back_substitution_time_in_seconds = 0.0005 * i;
+    it.iteration_time_in_seconds = 0.02;
+    it.cumulative_time_in_seconds = 0.02 * (i + 1);
+    s.iterations.push_back(it);
+  }
+  s.num_linear_solves = 3; s.num_residual_evaluations = 7; s.num_jacobian_evaluations = 2;
+  s.total_time_in_seconds = 0.08; s.minimizer_time_in_seconds = 0.07; s.preprocessor_time_in_seconds = 0.01;
+  BalProblemSoA<double> p;
+  p.nc = 3; p.nl = 2;
+  p.lm_off = {0, 2, 5}; p.obs_cam = {0, 1, 0, 1, 2}; p.obs_xy.assign(10, 0.0);
+  const DatasetSummary ds = summarize_problem<double>(p, "selftest \"quoted\" path");
+  PipelineTimingSummary pt;
+  pt.load_time = 0.5; pt.optimize_time = 0.08;
+  return write_ba_log(path, ds, pt, s) ? 0 : 1;
 }
 
 int main(int argc, char** argv) {
@@ -79,6 +109,7 @@ int main(int argc, char** argv) {
     else if (a == "--loader") { const std::string v = next(); if (v != "parallel" && v != "map") { std::cerr << "--loader parallel|map\n"; return 2; } parallel_loader = v == "parallel"; }
     else if (a == "--num-threads") num_threads = std::stoi(next());
     else if (a == "--dump-problem") dump = next();
+    else if (a == "--selftest-log") return selftest_log(next());
     else if (a == "--help" || a == "-h") { std::cout << "usage: bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI] ...\n"; return 0; }
     else { std::cerr << "unknown option " << a << "\n"; return 2; }
   }

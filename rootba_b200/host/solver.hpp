@@ -6,6 +6,7 @@
 //   bundle_adjust_manual <-> optimize_lm_ours         (src/rootba/solver/bal_bundle_adjustment.cpp:249-544)
 #pragma once
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <limits>
@@ -58,11 +59,13 @@ struct IterationSummary {
   double stage1_time_in_seconds = 0, stage2_time_in_seconds = 0, compute_preconditioner_time_in_seconds = 0,
          solve_reduced_system_time_in_seconds = 0, back_substitution_time_in_seconds = 0, update_cameras_time_in_seconds = 0,
          residual_evaluation_time_in_seconds = 0;
+  double iteration_time_in_seconds = 0, cumulative_time_in_seconds = 0;  // wall clock, like rootba::Timer (bal_bundle_adjustment.cpp:315-316)
 };
 struct SolverSummary {
   std::vector<IterationSummary> iterations;
   std::string termination_type = "NO_CONVERGENCE", message;
   int num_linear_solves = 0, num_residual_evaluations = 0, num_jacobian_evaluations = 0;
+  double preprocessor_time_in_seconds = 0, minimizer_time_in_seconds = 0, total_time_in_seconds = 0;  // :286, :530-532
 };
 
 template <class S> struct Abi;
@@ -183,7 +186,19 @@ void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSu
   const Scalar min_lambda(1.0 / o.max_trust_region_radius), max_lambda(1.0 / o.min_trust_region_radius);
   const Scalar vee_factor(o.vee_factor), initial_vee(o.initial_vee);
   Scalar lambda(1.0 / o.initial_trust_region_radius), lambda_vee(initial_vee);
+  using clock = std::chrono::steady_clock;
+  const auto since = [](clock::time_point t) { return std::chrono::duration<double>(clock::now() - t).count(); };
+  const auto t_total = clock::now();
   auto linearizor = LinearizorQR<Scalar, Problem>::create(bal_problem, o, &summary);
+  summary.preprocessor_time_in_seconds = since(t_total);
+  const auto t_minimizer = clock::now();
+  auto t_iter = clock::now();
+  const auto log_iteration = [&](IterationSummary& s) {  // finish_iteration (bal_bundle_adjustment.cpp:56-88)
+    s.iteration_time_in_seconds = since(t_iter);
+    s.cumulative_time_in_seconds = since(t_total);
+    t_iter = clock::now();
+    summary.iterations.push_back(s);
+  };
   auto cost_of = [&](const ResidualInfo& ri) {
     switch (o.optimized_cost) {
       case SolverOptions::OptimizedCost::ERROR: return ri.all.error;
@@ -205,7 +220,7 @@ void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSu
     if (it == 0) {
       it_summary.cost = ri; it_summary.trust_region_radius = 1 / (double)lambda;
       it_summary.step_is_successful = it_summary.step_is_valid = true;
-      summary.iterations.push_back(it_summary);
+      log_iteration(it_summary);
       ++it;
       continue;
     }
@@ -221,7 +236,7 @@ void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSu
       if (!finite) {
         lambda = lambda_vee * lambda; lambda_vee *= vee_factor;
         it_summary.trust_region_radius = 1 / (double)lambda;
-        summary.iterations.push_back(it_summary);
+        log_iteration(it_summary);
         ++it;
         if (lambda > max_lambda) { terminated = true; summary.message = "Solver did not converge and reached maximum damping lambda"; }
         continue;
@@ -251,7 +266,7 @@ void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSu
         const ResidualInfo& prev = summary.iterations.back().cost;
         const bool use_all = o.optimized_cost == SolverOptions::OptimizedCost::ERROR;
         const double pc = use_all ? prev.all.error : prev.valid.error, cc = use_all ? ri2.all.error : ri2.valid.error;
-        summary.iterations.push_back(it_summary);
+        log_iteration(it_summary);
         ++it;
         if (std::abs(pc - cc) <= o.function_tolerance * cc) { terminated = true; summary.termination_type = "CONVERGENCE"; summary.message = "Function tolerance reached."; }
         break;
@@ -259,7 +274,7 @@ void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSu
         if (!quiet) std::printf("\t[%s] error: %.4e, lambda: %.1e, cg_iter: %d\n", it_summary.step_is_valid ? "Reject" : "Invalid", ri2.all.error, (double)lambda, it_summary.linear_solver_iterations);
         lambda = lambda_vee * lambda; lambda_vee *= vee_factor;
         it_summary.trust_region_radius = 1 / (double)lambda;
-        summary.iterations.push_back(it_summary);
+        log_iteration(it_summary);
         linearizor->restore();  // bal_problem.restore() (:509)
         ++it;
         if (lambda > max_lambda) { terminated = true; summary.message = "Solver did not converge and reached maximum damping lambda"; }
@@ -268,6 +283,8 @@ void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSu
   }
   if (!terminated) summary.message = "Solver did not converge after maximum number of " + std::to_string(max_lm_iter) + " iterations";
   linearizor->download_state();
+  summary.minimizer_time_in_seconds = since(t_minimizer);
+  summary.total_time_in_seconds = since(t_total);
   if (!quiet) std::printf("%s: %s\n", summary.termination_type.c_str(), summary.message.c_str());
 }
 

@@ -148,6 +148,53 @@ def test_abi_loader_matches_map_loader_and_oracle(tmp_path):
         rb.BalProblem.load_bal(str(tmp_path / "missing.txt"))
 
 
+def _load_ba_log(path):
+    """ba_log.json as the reference's python/rootba/log.py reads it: top-level columns -> numpy arrays, `_static` nested"""
+    d = json.load(open(path))
+    assert d["_type"] == "rootba"
+    cols = {k: np.array(v) for k, v in d.items() if not k.startswith("_")}
+    return cols, d["_static"]
+
+
+def test_ba_log_has_the_reference_layout(tmp_path):
+    """`bal_qr` writes ba_log.json in the reference's format (bal/ba_log.hpp:139-252, ba_log.cpp:62-150): the field lists
+    come from tests/golden/ba_log_fields.json (extracted from the reference header by tests/golden/make_ba_log_fields.py);
+    the values follow log_summary (bal/ba_log_utils.cpp:97-166) and finish_solve (bal_bundle_adjustment.cpp:117-140)."""
+    _build()
+    out = str(tmp_path / "ba_log.json")
+    subprocess.check_call([BAL_QR, "--selftest-log", out])
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ba_log_fields.json")))["structs"]
+    raw = json.load(open(out))
+    cols, static = _load_ba_log(out)
+    names = lambda s: [f["name"] for f in golden[s]]
+    assert [k for k in raw if not k.startswith("_")] == names("BaIteration")       # same columns, same order
+    assert list(static) == names("Static")
+    assert list(static["problem_info"]) == names("ProblemInfo") and list(static["timing"]) == names("PipelineTiming")
+    assert list(static["solver"]) == names("BaSolver")
+    assert list(static["problem_info"]["per_lm_obs"]) == names("Stats") == list(static["problem_info"]["per_host_lms"])
+    n = len(cols["iteration"])
+    assert n == 4 and all(len(v) == n for v in cols.values())
+    for f in golden["BaIteration"]:  # JSON types follow the C++ member types
+        v = raw[f["name"]][0]
+        want = {"bool": bool, "int": int, "uint64_t": int, "double": (int, float), "std::string": str}[f["type"]]
+        assert isinstance(v, want) and (f["type"] == "bool" or not isinstance(v, bool)), f
+    # the fabricated run: accepted, rejected, accepted.  A rejected iteration repeats the previous cost columns
+    # ("for monotonic plots", ba_log_utils.cpp:119-137); cost_change is "previous logged cost - this cost"
+    assert cols["step_is_successful"].tolist() == [True, True, False, True]
+    assert cols["cost"].tolist() == [100.0, 40.0, 40.0, 39.99999]
+    assert np.allclose(cols["cost_change"], [0, 60, 0, 55 - 39.99999])
+    assert cols["relative_decrease"][2] == 0 and cols["linear_solver_type"].tolist() == ["", "bal_qr", "bal_qr", "bal_qr"]
+    assert np.allclose(cols["step_solver_time"], cols["stage2_time"] + cols["solve_reduced_system_time"] + cols["back_substitution_time"])
+    sol = static["solver"]
+    assert (sol["solver_type"], sol["termination_type"], sol["num_successful_steps"], sol["num_unsuccessful_steps"]) == ("bal_qr", 0, 2, 1)
+    assert sol["linear_solver_time_in_seconds"] == pytest.approx(cols["step_solver_time"].sum())
+    pi = static["problem_info"]
+    assert (pi["type"], pi["num_cameras"], pi["num_landmarks"], pi["num_observations"]) == ("bal", 3, 2, 5)
+    assert pi["per_lm_obs"] == {"mean": 2.5, "min": 2, "max": 3, "stddev": 0.5} and pi["rcs_sparsity"] == 0
+    assert pi["input_path"] == 'selftest "quoted" path'
+    assert static["timing"]["total"] == pytest.approx(0.58)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("use_double", [True, False])
 def test_bal_qr_matches_python_host(tmp_path, use_double):
@@ -161,15 +208,19 @@ def test_bal_qr_matches_python_host(tmp_path, use_double):
     log = str(tmp_path / "ba_log.json")
     args = [BAL_QR, "--input", path, "--max-num-iterations", "4", "--log-path", log] + ([] if use_double else ["--no-use-double"])
     subprocess.check_call(args, stdout=subprocess.DEVNULL)
-    its = json.load(open(log))["_iterations"]
+    cols, static = _load_ba_log(log)
     d = orc.load_bal(path, normalize=True)
     arrays = BalArrays(d["cams"], d["lms"], d["lm_off"], d["obs_cam"], d["obs_xy"])
     dtype = np.float64 if use_double else np.float32
     bp = rb.BalProblem.from_arrays(arrays, dtype)
     summ = rb.bundle_adjust_manual(bp, rb.SolverOptions(max_num_iterations=4))
-    assert len(its) == len(summ["iterations"])
-    for a, b in zip(its, summ["iterations"]):
-        cb = b["cost"]["all"]["error"]
+    assert len(cols["iteration"]) == len(summ["iterations"])
+    assert static["problem_info"]["num_observations"] == arrays.nobs and static["solver"]["solver_type"] == "bal_qr"
+    prev = None
+    for k, b in enumerate(summ["iterations"]):
+        # a rejected iteration repeats the previous cost in the log (ba_log_utils.cpp:119-137)
+        cb = b["cost"]["all"]["error"] if (b["step_is_successful"] or prev is None) else prev
+        prev = cb
         # the two hosts load the file with independent loaders (inputs differ in the last ulp), so the f64 trajectories
         # agree to ~1e-7 after a few LM iterations (threshold-based PCG stopping amplifies the ulp), not to 1e-9
-        assert abs(a["cost"] - cb) <= (1e-6 if use_double else 5e-3) * cb + 1e-12 * its[0]["cost"]
+        assert abs(cols["cost"][k] - cb) <= (1e-6 if use_double else 5e-3) * cb + 1e-12 * cols["cost"][0]
