@@ -445,6 +445,10 @@ def bench_ours(args):
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "cg_iterations": cg_log, "final_cost": final_cost,
         }
+        # also report microseconds per PCG iteration (solve_reduced_system_time over the PCG iterations)
+        n_cg = sum(int(c) for c in cg_log if c is not None)
+        out["pcg"] = {"iterations": n_cg,
+                      "us_per_iteration": (1e6 * phase["solve_reduced_system_time"] / n_cg) if n_cg > 0 else None}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -1244,7 +1244,7 @@ __device__ __forceinline__ void matvec_item(const DevPtrs<S>& D, const MatvecIte
                                             S* xs, const S* __restrict__ xvec) {
   using V2 = typename ST<S>::V2;
   const int n = T.n, G = T.G;
-  const int g = lane / G, j = lane - g * G, W = 32 / G;
+  const int g = lane / G, j = lane - g * G;
   const int ncols = 9 * n;
   const int CS = (2 * G * KP) | 1;
   // zero padding columns, gather x_red of the W landmarks (coalesced runs of 9)
