@@ -1,6 +1,7 @@
 """CPU-side checks of the C-ABI library: it loads without a GPU, exports every symbol the public header
 declares, refuses to run without a device (no CPU fallback), and its host-only helpers work."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -80,3 +81,22 @@ def test_layout_rejects_unsorted_and_short_tracks(tiny_problem):
     oc2 = np.ascontiguousarray(a.obs_cam, np.int32)
     pv2 = _lib.ProblemView(a.nc, a.nl, a.nobs, off2.ctypes.data, oc2.ctypes.data, xy.ctypes.data)
     assert L.rba_layout_selftest(C.byref(pv2), 0, 1, 8) != 0
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """the drop-in boundary is a C ABI: the header must compile as C99 (no C++ types) and a C program must link and run
+    against the library without a GPU"""
+    import subprocess
+    from conftest import ROOT
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "rootba_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n  rba_solver_opts o;\n  rba_default_solver_opts(&o);\n"
+        '  printf("%d %d %d\\n", (int)rba_abi_version(), (int)o.max_linear_solver_iterations, (int)sizeof(rba_solver_opts));\n'
+        "  return 0;\n}\n")
+    exe = str(tmp_path / "abi")
+    libdir = os.path.join(ROOT, "rootba_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L", libdir, "-lrootba_b200", "-Wl,-rpath," + libdir, "-o", exe])
+    out = subprocess.check_output([exe], text=True).split()
+    assert out[:2] == ["1", "500"] and int(out[2]) == C.sizeof(_lib.SolverOpts)  # ctypes mirror has the same size
