@@ -84,19 +84,23 @@ def test_layout_rejects_unsorted_and_short_tracks(tiny_problem):
 
 
 def test_header_is_plain_c_and_links(tmp_path):
-    """the drop-in boundary is a C ABI: the header must compile as C99 (no C++ types) and a C program must link and run
-    against the library without a GPU"""
+    """the drop-in boundary is a C ABI: the header must compile as C99 (no C++ types), a C program must link and run
+    against the library without a GPU, and the ctypes mirrors of the six structs must have the C sizes"""
     import subprocess
     from conftest import ROOT
+    structs = {"rba_problem_view": _lib.ProblemView, "rba_solver_opts": _lib.SolverOpts, "rba_residual_info": _lib.ResidualInfo,
+               "rba_cg_summary": _lib.CgSummary, "rba_stage_timings": _lib.StageTimings, "rba_workload_stats": _lib.WorkloadStats}
     src = tmp_path / "abi.c"
     src.write_text(
         '#include "rootba_b200.h"\n#include <stdio.h>\n'
         "int main(void) {\n  rba_solver_opts o;\n  rba_default_solver_opts(&o);\n"
-        '  printf("%d %d %d\\n", (int)rba_abi_version(), (int)o.max_linear_solver_iterations, (int)sizeof(rba_solver_opts));\n'
-        "  return 0;\n}\n")
+        '  printf("%d %d", (int)rba_abi_version(), (int)o.max_linear_solver_iterations);\n'
+        + "".join(f'  printf(" %d", (int)sizeof({n}));\n' for n in structs)
+        + '  printf("\\n");\n  return 0;\n}\n')
     exe = str(tmp_path / "abi")
     libdir = os.path.join(ROOT, "rootba_b200")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
                            "-L", libdir, "-lrootba_b200", "-Wl,-rpath," + libdir, "-o", exe])
     out = subprocess.check_output([exe], text=True).split()
-    assert out[:2] == ["1", "500"] and int(out[2]) == C.sizeof(_lib.SolverOpts)  # ctypes mirror has the same size
+    assert out[:2] == ["1", "500"]
+    assert [int(v) for v in out[2:]] == [C.sizeof(t) for t in structs.values()], dict(zip(structs, out[2:]))
