@@ -1,7 +1,7 @@
 // bal_qr: square-root BA solver on a BAL file with the GPU linearizor (counterpart of src/app/bal_qr.cpp:44-115).
 //   bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI]
 //          [--residual-robust-norm NONE|HUBER] [--residual-huber-parameter X] [--no-normalize] [--dump-problem out.bin]
-//          [--loader parallel|map] [--num-threads T]
+//          [--loader parallel|map] [--num-threads T] [--operator-form dense|implicit]
 //   --loader parallel (default): mmap + multi-threaded parse into flat arrays (bal_io_fast.hpp);
 //   --loader map: the reference-style fscanf + std::map loader (bal_problem.hpp).  Both give identical problems.
 #include <chrono>
@@ -105,6 +105,7 @@ int main(int argc, char** argv) {
     else if (a == "--residual-robust-norm") { const std::string v = next(); o.robust_norm = v == "HUBER" ? SolverOptions::RobustNorm::HUBER : SolverOptions::RobustNorm::NONE; }
     else if (a == "--residual-huber-parameter") o.huber_parameter = std::stod(next());
     else if (a == "--optimized-cost") { const std::string v = next(); o.optimized_cost = v == "ERROR" ? SolverOptions::OptimizedCost::ERROR : v == "ERROR_VALID" ? SolverOptions::OptimizedCost::ERROR_VALID : SolverOptions::OptimizedCost::ERROR_VALID_AVG; }
+    else if (a == "--operator-form") { const std::string v = next(); if (v != "dense" && v != "implicit") { std::cerr << "--operator-form dense|implicit\n"; return 2; } o.operator_form = v == "implicit"; }
     else if (a == "--log-path") log_path = next();
     else if (a == "--loader") { const std::string v = next(); if (v != "parallel" && v != "map") { std::cerr << "--loader parallel|map\n"; return 2; } parallel_loader = v == "parallel"; }
     else if (a == "--num-threads") num_threads = std::stoi(next());

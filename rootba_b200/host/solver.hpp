@@ -44,6 +44,7 @@ struct SolverOptions {
   RobustNorm robust_norm = RobustNorm::NONE;
   double huber_parameter = 1.0;
   int device = -1;
+  int operator_form = 0;  // not in the reference: 0 = dense Q2 panels (reference algorithm), 1 = implicit (rba_solver_opts.operator_form)
   bool use_projection_validity_check() const { return optimized_cost != OptimizedCost::ERROR; }  // solver_options.cpp:41-51
 };
 
@@ -161,6 +162,7 @@ class LinearizorQR {
     so.max_linear_solver_iterations = o.max_linear_solver_iterations;
     so.eta = o.eta;
     so.device = o.device;
+    so.operator_form = o.operator_form;
     bp.export_topology(lm_off_, obs_cam_, obs_xy_);
     rba_problem_view pv{bp.num_cameras(), bp.num_landmarks(), (int64_t)obs_cam_.size(), lm_off_.data(), obs_cam_.data(), obs_xy_.data()};
     check(Abi<Scalar>::create(&pv, &so, &h_));
