@@ -179,25 +179,22 @@ class LinearizorQR {
   std::vector<Scalar> obs_xy_;
 };
 
-// optimize_lm_ours (bal_bundle_adjustment.cpp:249-544): the host-serial LM loop, driving the GPU linearizor
-template <typename Scalar, class Problem>
-void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSummary* out = nullptr, bool quiet = false) {
-  SolverSummary local;
-  SolverSummary& summary = out ? *out : local;
-  summary = SolverSummary();
-  const Scalar min_lambda(1.0 / o.max_trust_region_radius), max_lambda(1.0 / o.min_trust_region_radius);
-  const Scalar vee_factor(o.vee_factor), initial_vee(o.initial_vee);
-  Scalar lambda(1.0 / o.initial_trust_region_radius), lambda_vee(initial_vee);
+// optimize_lm_ours (bal_bundle_adjustment.cpp:249-544): the host-serial LM loop.  Generic over the Linearizor (anything
+// with the members of rootba::Linearizor, solver/linearizor.hpp:56-82, plus backup / restore / download_state for the
+// device-resident state): the GPU LinearizorQR in production, an oracle-backed one in tests/cpp/lm_loop_cpu.cpp.
+template <typename Scalar, class Lin>
+void optimize_lm(Lin& lin, const SolverOptions& o, SolverSummary& summary, bool quiet = false) {
+  Lin* linearizor = &lin;
   using clock = std::chrono::steady_clock;
   const auto since = [](clock::time_point t) { return std::chrono::duration<double>(clock::now() - t).count(); };
   const auto t_total = clock::now();
-  auto linearizor = LinearizorQR<Scalar, Problem>::create(bal_problem, o, &summary);
-  summary.preprocessor_time_in_seconds = since(t_total);
-  const auto t_minimizer = clock::now();
+  const Scalar min_lambda(1.0 / o.max_trust_region_radius), max_lambda(1.0 / o.min_trust_region_radius);
+  const Scalar vee_factor(o.vee_factor), initial_vee(o.initial_vee);
+  Scalar lambda(1.0 / o.initial_trust_region_radius), lambda_vee(initial_vee);
   auto t_iter = clock::now();
   const auto log_iteration = [&](IterationSummary& s) {  // finish_iteration (bal_bundle_adjustment.cpp:56-88)
     s.iteration_time_in_seconds = since(t_iter);
-    s.cumulative_time_in_seconds = since(t_total);
+    s.cumulative_time_in_seconds = summary.preprocessor_time_in_seconds + since(t_total);
     t_iter = clock::now();
     summary.iterations.push_back(s);
   };
@@ -285,9 +282,21 @@ void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSu
   }
   if (!terminated) summary.message = "Solver did not converge after maximum number of " + std::to_string(max_lm_iter) + " iterations";
   linearizor->download_state();
-  summary.minimizer_time_in_seconds = since(t_minimizer);
-  summary.total_time_in_seconds = since(t_total);
+  summary.minimizer_time_in_seconds = since(t_total);
+  summary.total_time_in_seconds = summary.preprocessor_time_in_seconds + summary.minimizer_time_in_seconds;
   if (!quiet) std::printf("%s: %s\n", summary.termination_type.c_str(), summary.message.c_str());
+}
+
+// rootba::bundle_adjust_manual (bal_bundle_adjustment.cpp:546-569): create the linearizor, run the LM loop
+template <typename Scalar, class Problem>
+void bundle_adjust_manual(Problem& bal_problem, const SolverOptions& o, SolverSummary* out = nullptr, bool quiet = false) {
+  SolverSummary local;
+  SolverSummary& summary = out ? *out : local;
+  summary = SolverSummary();
+  const auto t0 = std::chrono::steady_clock::now();
+  auto linearizor = LinearizorQR<Scalar, Problem>::create(bal_problem, o, &summary);
+  summary.preprocessor_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  optimize_lm<Scalar>(*linearizor, o, summary, quiet);
 }
 
 }  // namespace rootba_b200

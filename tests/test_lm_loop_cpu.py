@@ -115,3 +115,61 @@ def test_python_lm_loop_equals_oracle_lm_loop(small_problem, hard_problem, dtype
     c1, l1 = ref.get_state()
     c2, l2 = drv.get_state()
     assert np.array_equal(c1, c2) and np.array_equal(l1, l2)
+
+
+# ---- the C++ host's LM loop (rootba_b200/host/solver.hpp::optimize_lm), same idea ------------------------------------
+
+CPP_CASES = [
+    ([], {}, False),
+    (["--float"], {}, False),
+    (["--jacobi"], {"preconditioner_type": 0}, False),
+    (["--float", "--huber", "2.0"], {"robust_norm": 1, "huber_parameter": 2.0}, False),
+    (["--optimized-cost", "ERROR_VALID"], {"optimized_cost": 1, "use_valid_projections_only": 1}, False),
+    (["--optimized-cost", "ERROR_VALID_AVG", "--float"], {"optimized_cost": 2, "use_valid_projections_only": 1}, False),
+    (["--givens"], {"use_householder": 0}, True),
+    ([], {}, True),
+    (["--float"], {}, True),
+    (["--min-relative-decrease", "0.5"], {"min_relative_decrease": 0.5}, True),
+    (["--initial-trust-region-radius", "1e12", "--min-trust-region-radius", "1e-3"],
+     {"initial_trust_region_radius": 1e12, "min_trust_region_radius": 1e-3}, True),
+]
+
+
+@pytest.mark.parametrize("flags,okw,hard", CPP_CASES)
+def test_cpp_lm_loop_equals_oracle_lm_loop(tmp_path, small_problem, hard_problem, flags, okw, hard):
+    """tests/cpp/lm_loop_cpu.cpp runs rootba_b200::optimize_lm (the loop `bal_qr` uses on the GPU) with an oracle-backed
+    Linearizor; the oracle's own loop on the arrays that driver loaded must give the same trajectory."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from rootba_b200 import _lib
+    from rootba_b200.synthetic import BalArrays, write_bal
+    from test_host_cpp import _read_dump
+    _lib.build()
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"])
+    prob = hard_problem if hard else small_problem
+    n_it = 12 if hard else 8
+    path, dump = str(tmp_path / "p.txt"), str(tmp_path / "arrays.bin")
+    write_bal(prob, path)
+    out = subprocess.check_output([os.path.join(ROOT, "tests", "cpp", "_build", "lm_loop_cpu"), "--input", path, "--dump", dump,
+                                   "--max-num-iterations", str(n_it)] + flags, text=True)
+    got = []
+    for line in out.splitlines():
+        t = line.split()
+        if t[0] == "it":
+            got.append({"iteration": int(t[1]), "cost": float(t[3]), "cost_valid": float(t[5]), "ok": int(t[7]), "valid": int(t[9]),
+                        "trr": float(t[11]), "rho": float(t[13]), "cg": int(t[15])})
+    cams, lms, off, oc, xy = _read_dump(dump)
+    dtype = np.float32 if "--float" in flags else np.float64
+    ref = orc.Oracle(BalArrays(cams, lms, off, oc, xy), dtype, orc.default_options(max_num_iterations=n_it, num_threads=1, **okw))
+    rows, _ = ref.optimize()
+    assert len(got) == len(rows)
+    for a, b in zip(got, rows):
+        assert a["iteration"] == int(b["iteration"]) and a["ok"] == int(bool(b["step_is_successful"])), a
+        # same source, same compiler flags: the arithmetic is identical.  A rejected step logs the rejected cost on both sides.
+        assert a["cost"] == pytest.approx(b["cost"], rel=1e-13) and a["cost_valid"] == pytest.approx(b["cost_valid"], rel=1e-13)
+        assert a["trr"] == pytest.approx(b["trust_region_radius"], rel=1e-13)
+        if a["iteration"] > 0:
+            assert a["cg"] == int(b["cg_iterations"]) and a["rho"] == pytest.approx(b["relative_decrease"], rel=1e-9, abs=1e-12)
+    if hard:
+        assert not all(a["ok"] for a in got[1:])
