@@ -6,3 +6,4 @@ Python here is only the host-side mirror of the reference interface and the synt
 from .linearizor import (BalProblem, LinearizorQR, ResidualOptions, SolverOptions, bundle_adjust_manual,  # noqa: F401
                          nccl_unique_id, partition_landmarks)
 from ._lib import RbaError, build  # noqa: F401
+from .ba_log import make_ba_log, save_ba_log, summarize_problem  # noqa: F401

@@ -83,7 +83,9 @@ inline std::string json_num(double v) {
   if (!std::isfinite(v)) return "null";  // nlohmann::json dumps NaN / inf as null
   std::ostringstream o;
   o << std::setprecision(17) << v;
-  return o.str();
+  std::string t = o.str();
+  if (t.find_first_of(".eE") == std::string::npos) t += ".0";  // a double stays a JSON float (nlohmann::json prints 100.0)
+  return t;
 }
 template <class It, class F>
 void column(std::ostream& f, const char* name, const std::vector<It>& rows, F&& value, bool last = false) {

@@ -195,6 +195,49 @@ def test_ba_log_has_the_reference_layout(tmp_path):
     assert static["timing"]["total"] == pytest.approx(0.58)
 
 
+def test_python_ba_log_writer_agrees_with_the_cpp_one(tmp_path):
+    """rootba_b200.ba_log (Python host) and rootba_b200/host/ba_log.hpp (C++ host) on the same fabricated run"""
+    import types
+    import rootba_b200 as rb
+    from rootba_b200.ba_log import BA_ITERATION_FIELDS
+    _build()
+    out = str(tmp_path / "cpp.json")
+    subprocess.check_call([BAL_QR, "--selftest-log", out])
+    cpp = json.load(open(out))
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "ba_log_fields.json")))["structs"]
+    assert list(BA_ITERATION_FIELDS) == [f["name"] for f in golden["BaIteration"]]
+    costs, ok = [100.0, 40.0, 55.0, 39.99999], [True, True, False, True]
+    its = []
+    for i in range(4):  # the summary `bal_qr --selftest-log` fabricates (rootba_b200/host/bal_qr.cpp)
+        its.append({"iteration": i, "cost": {"all": {"num_obs": 10, "error": costs[i], "residual_sum": 10 * np.sqrt(costs[i])},
+                                             "valid": {"num_obs": 9, "error": 0.9 * costs[i], "residual_sum": 9 * np.sqrt(costs[i])}},
+                    "step_is_valid": True, "step_is_successful": ok[i], "trust_region_radius": 1e4 * (i + 1),
+                    "relative_decrease": 0.5 if i else 0.0, "linear_solver_iterations": 3 * i, "stage1_time": 0.001 if i else 0.0,
+                    "stage2_time": 0.002 * i, "solve_reduced_system_time": 0.01 * i, "back_substitution_time": 0.0005 * i,
+                    "iteration_time": 0.02, "cumulative_time": 0.02 * (i + 1)})
+    summary = {"iterations": its, "termination_type": "CONVERGENCE", "message": "Function tolerance reached.", "num_linear_solves": 3,
+               "num_residual_evaluations": 7, "num_jacobian_evaluations": 2, "total_time": 0.08, "minimizer_time": 0.07, "preprocessor_time": 0.01}
+    prob = types.SimpleNamespace(lm_off=np.array([0, 2, 5]), obs_cam=np.array([0, 1, 0, 1, 2]), num_cameras=lambda: 3,
+                                 num_landmarks=lambda: 2, num_observations=lambda: 5)
+    py = rb.make_ba_log(summary, rb.summarize_problem(prob, 'selftest "quoted" path'), {"load": 0.5, "optimize": 0.08})
+    py = json.loads(json.dumps(py))  # through JSON, like the file
+    assert list(py) == list(cpp)
+    for k in cpp:
+        if k.startswith("_"):
+            continue
+        assert len(py[k]) == len(cpp[k]) == 4
+        for a, b in zip(py[k], cpp[k]):
+            assert (a == pytest.approx(b, rel=1e-15, abs=1e-300)) if isinstance(b, float) else (a == b and type(a) is type(b)), (k, a, b)
+    assert py["_type"] == cpp["_type"]
+    for sect in ("problem_info", "timing", "solver"):
+        assert list(py["_static"][sect]) == list(cpp["_static"][sect])
+        for k, b in cpp["_static"][sect].items():
+            a = py["_static"][sect][k]
+            assert a == (pytest.approx(b, rel=1e-12) if isinstance(b, float) else b), (sect, k, a, b)
+    rb.save_ba_log(str(tmp_path / "py.json"), summary, prob, "x")
+    assert json.load(open(tmp_path / "py.json"))["_static"]["problem_info"]["input_path"] == "x"
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("use_double", [True, False])
 def test_bal_qr_matches_python_host(tmp_path, use_double):
