@@ -15,6 +15,7 @@ import ctypes as C
 import os
 import dataclasses
 import math
+import time
 
 import numpy as np
 
@@ -356,12 +357,22 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
     vee_factor, initial_vee = S(o.vee_factor), S(o.initial_vee)
     lam = S(1.0 / o.initial_trust_region_radius)
     lambda_vee = initial_vee
-    summary = {"iterations": [], "num_linear_solves": 0, "termination_type": "NO_CONVERGENCE", "message": ""}
+    summary = {"iterations": [], "num_linear_solves": 0, "num_residual_evaluations": 0, "num_jacobian_evaluations": 0,
+               "termination_type": "NO_CONVERGENCE", "message": ""}
+    t_total = time.perf_counter()
     own = linearizor is None
     if own:
         linearizor = LinearizorQR.create(bal_problem, o, summary)
         if comm_setup is not None:
             comm_setup(linearizor)
+    summary["preprocessor_time"] = time.perf_counter() - t_total
+    t_iter = [time.perf_counter()]
+
+    def log_iteration(s):  # finish_iteration (bal_bundle_adjustment.cpp:56-88): wall-clock stamps, then push
+        now = time.perf_counter()
+        s["iteration_time"], s["cumulative_time"] = now - t_iter[0], now - t_total
+        t_iter[0] = now
+        summary["iterations"].append(s)
     terminated = False
     it = 0
     max_lm_iter = o.max_num_iterations
@@ -370,16 +381,18 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
             it_summary = {"iteration": it}
             linearizor.start_iteration(it_summary)
             ri = linearizor.compute_error()
+            summary["num_residual_evaluations"] += 1
             if not ri["is_numerically_valid"]:
                 raise RbaError(1, "did not expect numerical failure during linearization")  # :307-308
             if it == 0:
                 linearizor.finish_iteration()
                 it_summary.update(cost=ri, trust_region_radius=1 / float(lam), step_is_successful=True, step_is_valid=True,
                                   lam=float(lam))
-                summary["iterations"].append(it_summary)
+                log_iteration(it_summary)
                 it += 1
                 continue
             linearizor.linearize()
+            summary["num_jacobian_evaluations"] += 1
             j = 0
             while it <= max_lm_iter and not terminated:
                 if j > 0:
@@ -395,7 +408,7 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
                     lambda_vee = S(lambda_vee * vee_factor)
                     linearizor.finish_iteration()
                     it_summary["trust_region_radius"] = 1 / float(lam)
-                    summary["iterations"].append(it_summary)
+                    log_iteration(it_summary)
                     it += 1
                     if lam > max_lambda:
                         terminated = True
@@ -404,6 +417,7 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
                 bal_problem.backup()
                 l_diff = S(linearizor.apply(inc))
                 ri2 = linearizor.compute_error()
+                summary["num_residual_evaluations"] += 1
                 it_summary["cost"] = ri2
                 it_summary["l_diff"] = float(l_diff)
                 if not math.isfinite(float(l_diff)) or not ri2["is_numerically_valid"]:
@@ -425,7 +439,7 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
                     zero = {"all": {"num_obs": 0, "error": 0.0}, "valid": {"num_obs": 0, "error": 0.0}}
                     prev = _cost(summary["iterations"][-1].get("cost", zero), "ERROR" if o.optimized_cost == "ERROR" else "ERROR_VALID")
                     cur = _cost(ri2, "ERROR" if o.optimized_cost == "ERROR" else "ERROR_VALID")
-                    summary["iterations"].append(it_summary)
+                    log_iteration(it_summary)
                     it += 1
                     if abs(prev - cur) <= o.function_tolerance * cur:  # :174-201
                         terminated = True
@@ -439,7 +453,7 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
                     lambda_vee = S(lambda_vee * vee_factor)
                     linearizor.finish_iteration()
                     it_summary["trust_region_radius"] = 1 / float(lam)
-                    summary["iterations"].append(it_summary)
+                    log_iteration(it_summary)
                     bal_problem.restore()
                     it += 1
                     if lam > max_lambda:
@@ -448,6 +462,8 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
     if not terminated:
         summary["message"] = f"Solver did not converge after maximum number of {max_lm_iter} iterations"
     bal_problem.sync_from_device()
+    summary["total_time"] = time.perf_counter() - t_total
+    summary["minimizer_time"] = summary["total_time"] - summary["preprocessor_time"]
     if own:
         summary["stats"] = linearizor.stats()
         linearizor.close()
