@@ -175,6 +175,10 @@ int32_t rba_layout_selftest(const rba_problem_view* problem, int32_t rank, int32
  * correctly).  All values are double, as in the reference (cast to float happens after normalisation, :813-832). */
 typedef struct rba_bal_file rba_bal_file;
 int32_t rba_bal_load(const char* path, int32_t normalize, double scale, int32_t num_threads, rba_bal_file** out);
+/* BalProblem::filter_obs (bal_problem.cpp:471-505; BalDatasetOptions::init_depth_threshold): drop the observations whose
+ * landmark is closer than `threshold` in front of the camera, then the landmarks left with fewer than 2 observations
+ * (landmark indices are compacted).  Call after rba_bal_load, before rba_bal_dims / rba_bal_copy; threshold <= 0: no-op. */
+int32_t rba_bal_filter_obs(rba_bal_file* f, double threshold);
 /* sizes, to allocate the arrays for rba_bal_copy */
 int32_t rba_bal_dims(const rba_bal_file* f, int32_t* num_cameras, int32_t* num_landmarks, int64_t* num_observations);
 /* cams [10*Nc] (qx,qy,qz,qw,t,f,k1,k2 = Camera::params(), bal_problem.hpp:84-89), lms [3*Nl], lm_obs_offset [Nl+1],

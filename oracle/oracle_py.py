@@ -263,13 +263,15 @@ def invert_block9(block, diag=None, dtype=np.float64):
     return out.reshape(9, 9)
 
 
-def load_bal(path: str, normalize=True, scale=100.0):
-    """BAL text loader + default normalisation (double).  Returns a dict of arrays."""
+def load_bal(path: str, normalize=True, scale=100.0, init_depth_threshold=0.0):
+    """BAL text loader + default normalisation (double) + filter_obs (bal_problem.cpp:471-505).  Returns a dict of arrays."""
     nc, nl, nobs = C.c_int(), C.c_int(), C.c_int64()
     rc = lib().orc_bal_load(path.encode(), C.c_int(int(normalize)), C.c_double(scale), C.byref(nc),
                             C.byref(nl), C.byref(nobs))
     if rc != 0:
         raise RuntimeError(f"orc_bal_load failed rc={rc}")
+    if init_depth_threshold > 0:
+        lib().orc_bal_filter_obs(C.c_double(init_depth_threshold), C.byref(nl), C.byref(nobs))
     cams, lms = np.zeros((nc.value, 10)), np.zeros((nl.value, 3))
     off, oc, xy = np.zeros(nl.value + 1, np.int64), np.zeros(nobs.value, np.int32), np.zeros((nobs.value, 2))
     lib().orc_bal_get(_p(cams), _p(lms), _p(off), _p(oc), _p(xy))

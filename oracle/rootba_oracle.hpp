@@ -1412,4 +1412,38 @@ inline void normalize(BalData& D, double new_scale) {
   }
 }
 
+// ref: bal/bal_problem.cpp:471-505  filter_obs: drop observations whose landmark lies closer than `threshold` in front of
+// the camera (z of T_c_w * p_w), then drop landmarks left with fewer than 2 observations.  threshold <= 0: no-op.
+inline void filter_obs(BalData& D, double threshold) {
+  if (!(threshold > 0)) return;
+  BalData R;
+  R.nc = D.nc;
+  R.cams = D.cams;
+  R.lm_off.push_back(0);
+  for (int l = 0; l < D.nl; ++l) {
+    const double* p = D.lms.data() + 3 * (size_t)l;
+    const size_t keep_from = R.obs_cam.size();
+    for (int64_t k = D.lm_off[l]; k < D.lm_off[l + 1]; ++k) {
+      const double* c = D.cams.data() + 10 * (size_t)D.obs_cam[k];
+      double Rm[9];
+      quat_to_rot(c, Rm);
+      const double z = Rm[6] * p[0] + Rm[7] * p[1] + Rm[8] * p[2] + c[6];
+      if (z < threshold) continue;
+      R.obs_cam.push_back(D.obs_cam[k]);
+      R.obs_xy.push_back(D.obs_xy[2 * k]);
+      R.obs_xy.push_back(D.obs_xy[2 * k + 1]);
+    }
+    if (R.obs_cam.size() - keep_from >= 2) {
+      R.lms.insert(R.lms.end(), p, p + 3);
+      R.lm_off.push_back((int64_t)R.obs_cam.size());
+    } else {
+      R.obs_cam.resize(keep_from);
+      R.obs_xy.resize(2 * keep_from);
+    }
+  }
+  R.nl = (int)R.lm_off.size() - 1;
+  R.nobs = (int64_t)R.obs_cam.size();
+  D = std::move(R);
+}
+
 }  // namespace orc

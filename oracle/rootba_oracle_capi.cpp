@@ -117,6 +117,11 @@ int orc_bal_load(const char* path, int do_normalize, double scale, int* nc, int*
   *nc = g_bal.nc; *nl = g_bal.nl; *nobs = g_bal.nobs;
   return 0;
 }
+// filter_obs on the staged problem (after normalisation, like load_normalized_bal_problem); returns the new sizes
+void orc_bal_filter_obs(double threshold, int* nl, int64_t* nobs) {
+  filter_obs(g_bal, threshold);
+  *nl = g_bal.nl; *nobs = g_bal.nobs;
+}
 void orc_bal_get(double* cams, double* lms, int64_t* lm_off, int* obs_cam, double* obs_xy) {
   std::memcpy(cams, g_bal.cams.data(), g_bal.cams.size() * sizeof(double));
   std::memcpy(lms, g_bal.lms.data(), g_bal.lms.size() * sizeof(double));

@@ -904,6 +904,11 @@ int32_t rba_bal_load(const char* path, int32_t normalize, double scale, int32_t 
     return RBA_ERR_INVALID_ARGUMENT;
   }
 }
+int32_t rba_bal_filter_obs(rba_bal_file* f, double threshold) {
+  if (!f || threshold < 0) { rba::g_err = "bad arguments"; return RBA_ERR_INVALID_ARGUMENT; }  // the reference CHECK_GEs the threshold
+  f->p.filter_obs(threshold);
+  return RBA_OK;
+}
 int32_t rba_bal_dims(const rba_bal_file* f, int32_t* nc, int32_t* nl, int64_t* nobs) {
   if (!f) return RBA_ERR_INVALID_ARGUMENT;
   if (nc) *nc = f->p.nc;

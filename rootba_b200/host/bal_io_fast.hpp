@@ -147,6 +147,38 @@ class BalProblemSoA {
     }
   }
 
+  // ref: bal_problem.cpp:471-505: drop observations with depth (z of T_c_w * p_w) below the threshold, then landmarks with
+  // fewer than 2 observations left; threshold <= 0 is a no-op.  Same arithmetic as BalProblem::filter_obs (bal_problem.hpp).
+  void filter_obs(double threshold) {
+    if (!(threshold > 0)) return;
+    std::vector<Scalar> nlms, nxy;
+    std::vector<int64_t> noff(1, 0);
+    std::vector<int32_t> ncam;
+    for (int l = 0; l < nl; ++l) {
+      const Scalar* p = lms.data() + 3 * (size_t)l;
+      const size_t keep_from = ncam.size();
+      for (int64_t k = lm_off[l]; k < lm_off[l + 1]; ++k) {
+        const Scalar* c = cams.data() + (size_t)CAM_STATE_SIZE * obs_cam[k];
+        Scalar R[9];
+        quat_to_rot(c, R);
+        const Scalar z = R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + c[6];
+        if (z < Scalar(threshold)) continue;
+        ncam.push_back(obs_cam[k]);
+        nxy.push_back(obs_xy[2 * k]);
+        nxy.push_back(obs_xy[2 * k + 1]);
+      }
+      if (ncam.size() - keep_from >= 2) {
+        nlms.insert(nlms.end(), p, p + 3);
+        noff.push_back((int64_t)ncam.size());
+      } else {
+        ncam.resize(keep_from);
+        nxy.resize(2 * keep_from);
+      }
+    }
+    lms.swap(nlms); obs_xy.swap(nxy); lm_off.swap(noff); obs_cam.swap(ncam);
+    nl = (int)lm_off.size() - 1;
+  }
+
   template <typename Scalar2>
   BalProblemSoA<Scalar2> copy_cast() const {  // bal_problem.hpp:201-219
     BalProblemSoA<Scalar2> r;
@@ -345,9 +377,10 @@ inline BalProblemSoA<double> load_bal_parallel(const std::string& path, int nthr
 // ref: bal_problem.cpp:773-852: load + normalise in double, then cast
 template <class Scalar>
 BalProblemSoA<Scalar> load_normalized_bal_problem_parallel(const std::string& path, bool normalize = true, double scale = 100.0,
-                                                           int nthreads = 0) {
+                                                           int nthreads = 0, double init_depth_threshold = 0.0) {
   BalProblemSoA<double> p = load_bal_parallel(path, nthreads);
   if (normalize) p.normalize(scale);
+  p.filter_obs(init_depth_threshold);  // (the reference perturbs between the two, bal_problem.cpp:818-824; no perturbation here)
   return p.template copy_cast<Scalar>();
 }
 

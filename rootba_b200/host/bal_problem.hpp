@@ -98,6 +98,25 @@ class BalProblem {
     }
   }
 
+  // ref: bal_problem.cpp:471-505
+  void filter_obs(double threshold) {
+    if (!(threshold > 0)) return;
+    for (auto& lm : landmarks_) {
+      for (auto it = lm.obs.cbegin(); it != lm.obs.cend();) {
+        const auto& c = cameras_.at(it->first).params;
+        Scalar R[9];
+        quat_to_rot(c.data(), R);
+        const Scalar z = R[6] * lm.p_w[0] + R[7] * lm.p_w[1] + R[8] * lm.p_w[2] + c[6];
+        if (z < Scalar(threshold)) it = lm.obs.erase(it);
+        else ++it;
+      }
+    }
+    std::vector<Landmark> kept;
+    for (auto& lm : landmarks_)
+      if (lm.obs.size() >= 2) kept.push_back(std::move(lm));
+    landmarks_ = std::move(kept);
+  }
+
   // ref: bal_problem.cpp:590-608
   void backup() { cameras_backup_ = cameras_; landmarks_backup_.resize(landmarks_.size()); for (size_t i = 0; i < landmarks_.size(); ++i) landmarks_backup_[i] = landmarks_[i].p_w; }
   void restore() { cameras_ = cameras_backup_; for (size_t i = 0; i < landmarks_.size(); ++i) landmarks_[i].p_w = landmarks_backup_[i]; }
@@ -183,10 +202,12 @@ class BalProblem {
 
 // ref: bal_problem.cpp:773-852 load_normalized_bal_problem: always load + normalise in double, then cast
 template <class Scalar>
-BalProblem<Scalar> load_normalized_bal_problem(const std::string& path, bool normalize = true, double scale = 100.0) {
+BalProblem<Scalar> load_normalized_bal_problem(const std::string& path, bool normalize = true, double scale = 100.0,
+                                              double init_depth_threshold = 0.0) {
   BalProblem<double> p;
   p.load_bal(path);
   if (normalize) p.normalize(scale);
+  p.filter_obs(init_depth_threshold);
   return p.template copy_cast<Scalar>();
 }
 

@@ -1,7 +1,7 @@
 // bal_qr: square-root BA solver on a BAL file with the GPU linearizor (counterpart of src/app/bal_qr.cpp:44-115).
 //   bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI]
 //          [--residual-robust-norm NONE|HUBER] [--residual-huber-parameter X] [--no-normalize] [--dump-problem out.bin]
-//          [--loader parallel|map] [--num-threads T] [--operator-form dense|implicit]
+//          [--loader parallel|map] [--num-threads T] [--operator-form dense|implicit] [--init-depth-threshold Z]
 //   --loader parallel (default): mmap + multi-threaded parse into flat arrays (bal_io_fast.hpp);
 //   --loader map: the reference-style fscanf + std::map loader (bal_problem.hpp).  Both give identical problems.
 #include <chrono>
@@ -22,15 +22,15 @@ template <class S, class Problem>
 int solve_and_log(Problem& problem, const SolverOptions& o, const std::string& log_path, const std::string& input, double load_time);
 
 template <class S>
-int run(const std::string& input, bool normalize, const SolverOptions& o, const std::string& log_path, bool parallel_loader, int num_threads) {
+int run(const std::string& input, bool normalize, const SolverOptions& o, const std::string& log_path, bool parallel_loader, int num_threads, double depth_thr) {
   const auto t0 = std::chrono::steady_clock::now();
   if (parallel_loader) {
-    auto problem = load_normalized_bal_problem_parallel<S>(input, normalize, 100.0, num_threads);
+    auto problem = load_normalized_bal_problem_parallel<S>(input, normalize, 100.0, num_threads, depth_thr);
     std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s' in %.3fs (parallel loader)\n", problem.num_cameras(),
                 problem.num_landmarks(), (long long)problem.num_observations(), input.c_str(), seconds_since(t0));
     return solve_and_log<S>(problem, o, log_path, input, seconds_since(t0));
   }
-  auto problem = load_normalized_bal_problem<S>(input, normalize);
+  auto problem = load_normalized_bal_problem<S>(input, normalize, 100.0, depth_thr);
   std::printf("Loaded BAL problem (%d cams, %d lms, %lld obs) from '%s' in %.3fs (map loader)\n", problem.num_cameras(),
               problem.num_landmarks(), (long long)problem.num_observations(), input.c_str(), seconds_since(t0));
   return solve_and_log<S>(problem, o, log_path, input, seconds_since(t0));
@@ -89,6 +89,7 @@ int main(int argc, char** argv) {
   std::string input, dump, log_path = "ba_log.json";
   bool use_double = true, normalize = true, parallel_loader = true;
   int num_threads = 0;
+  double depth_thr = 0.0;  // BalDatasetOptions::init_depth_threshold (bal_dataset_options.hpp:82)
   SolverOptions o;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -109,6 +110,7 @@ int main(int argc, char** argv) {
     else if (a == "--log-path") log_path = next();
     else if (a == "--loader") { const std::string v = next(); if (v != "parallel" && v != "map") { std::cerr << "--loader parallel|map\n"; return 2; } parallel_loader = v == "parallel"; }
     else if (a == "--num-threads") num_threads = std::stoi(next());
+    else if (a == "--init-depth-threshold") depth_thr = std::stod(next());
     else if (a == "--dump-problem") dump = next();
     else if (a == "--selftest-log") return selftest_log(next());
     else if (a == "--help" || a == "-h") { std::cout << "usage: bal_qr --input <bal file> [--no-use-double] [--max-num-iterations N] [--preconditioner-type JACOBI|SCHUR_JACOBI] ...\n"; return 0; }
@@ -121,11 +123,11 @@ int main(int argc, char** argv) {
       int nc = 0, nl = 0;
       const auto t0 = std::chrono::steady_clock::now();
       if (parallel_loader) {
-        auto p = load_normalized_bal_problem_parallel<double>(input, normalize, 100.0, num_threads);
+        auto p = load_normalized_bal_problem_parallel<double>(input, normalize, 100.0, num_threads, depth_thr);
         std::printf("load time %.3fs (parallel loader)\n", seconds_since(t0));
         p.export_topology(off, oc, xy); p.export_state(c, l); nc = p.num_cameras(); nl = p.num_landmarks();
       } else {
-        auto p = load_normalized_bal_problem<double>(input, normalize);
+        auto p = load_normalized_bal_problem<double>(input, normalize, 100.0, depth_thr);
         std::printf("load time %.3fs (map loader)\n", seconds_since(t0));
         p.export_topology(off, oc, xy); p.export_state(c, l); nc = p.num_cameras(); nl = p.num_landmarks();
       }
@@ -137,7 +139,7 @@ int main(int argc, char** argv) {
       return 0;
     }
     o.use_double = use_double;
-    return use_double ? run<double>(input, normalize, o, log_path, parallel_loader, num_threads) : run<float>(input, normalize, o, log_path, parallel_loader, num_threads);
+    return use_double ? run<double>(input, normalize, o, log_path, parallel_loader, num_threads, depth_thr) : run<float>(input, normalize, o, log_path, parallel_loader, num_threads, depth_thr);
   } catch (const std::exception& e) {
     std::cerr << "FATAL: " << e.what() << "\n";
     return 1;

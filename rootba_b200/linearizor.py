@@ -84,13 +84,16 @@ class BalProblem:
         return cls(arrays.cams, arrays.lms, arrays.lm_off, arrays.obs_cam, arrays.obs_xy, dtype)
 
     @classmethod
-    def load_bal(cls, path: str, dtype=np.float64, normalize: bool = True, scale: float = 100.0, num_threads: int = 0) -> "BalProblem":
+    def load_bal(cls, path: str, dtype=np.float64, normalize: bool = True, scale: float = 100.0, num_threads: int = 0,
+                 init_depth_threshold: float = 0.0) -> "BalProblem":
         """load_normalized_bal_problem (bal/bal_problem.cpp:773-852) through the library's multi-threaded BAL parser
         (rba_bal_load): load + normalise in double, then cast to dtype."""
         L = _lib.lib()
         f = C.c_void_p()
         check(L.rba_bal_load(os.fsencode(path), int(normalize), C.c_double(scale), int(num_threads), C.byref(f)))
         try:
+            if init_depth_threshold > 0:  # BalDatasetOptions::init_depth_threshold -> filter_obs (bal_problem.cpp:471-505, :826)
+                check(L.rba_bal_filter_obs(f, C.c_double(init_depth_threshold)))
             nc, nl, nobs = C.c_int32(), C.c_int32(), C.c_int64()
             check(L.rba_bal_dims(f, C.byref(nc), C.byref(nl), C.byref(nobs)))
             cams, lms = np.empty((nc.value, 10)), np.empty((nl.value, 3))

@@ -148,6 +148,45 @@ def test_abi_loader_matches_map_loader_and_oracle(tmp_path):
         rb.BalProblem.load_bal(str(tmp_path / "missing.txt"))
 
 
+@pytest.mark.parametrize("threshold", [0.0, 60.0, 95.0, 1e6])
+def test_filter_obs_matches_oracle_and_numpy(tmp_path, threshold):
+    """BalProblem::filter_obs (bal_problem.cpp:471-505, BalDatasetOptions::init_depth_threshold) in the four places it exists --
+    both C++ loaders (byte-compared), the C ABI (rba_bal_filter_obs via BalProblem.load_bal) and the oracle -- against a numpy
+    statement of the rule: keep an observation iff z(T_c_w p_w) >= threshold, keep a landmark iff >= 2 observations are left."""
+    import rootba_b200 as rb
+    from oracle import oracle_py as orc
+    from rootba_b200.synthetic import quat_to_rot, synth_bal, write_bal
+    _build()
+    prob = synth_bal(15, 400, 4.0, seed=4, normalize_scale=None)
+    path = str(tmp_path / "p.txt")
+    write_bal(prob, path)
+    base = orc.load_bal(path, normalize=True)  # normalised, unfiltered: the input of filter_obs in the reference pipeline
+    R = quat_to_rot(base["cams"][:, :4])
+    lm_of_obs = np.repeat(np.arange(len(base["lm_off"]) - 1), np.diff(base["lm_off"]))
+    z = np.einsum("kj,kj->k", R[base["obs_cam"], 2, :], base["lms"][lm_of_obs]) + base["cams"][base["obs_cam"], 6]
+    keep_obs = z >= threshold if threshold > 0 else np.ones(len(z), bool)
+    n_left = np.bincount(lm_of_obs[keep_obs], minlength=len(base["lm_off"]) - 1)
+    keep_lm = n_left >= 2
+    keep = keep_obs & keep_lm[lm_of_obs]
+    want_off = np.concatenate([[0], np.cumsum(n_left[keep_lm])])
+    if threshold in (60.0, 95.0):
+        assert 0 < keep.sum() < len(keep) and keep_lm.sum() < len(keep_lm)  # the case really filters something
+    got = orc.load_bal(path, normalize=True, init_depth_threshold=threshold)
+    assert np.array_equal(got["lm_off"], want_off) and np.array_equal(got["obs_cam"], base["obs_cam"][keep])
+    assert np.array_equal(got["obs_xy"], base["obs_xy"][keep]) and np.array_equal(got["lms"], base["lms"][keep_lm])
+    dumps = {}
+    for loader in ("parallel", "map"):
+        out = str(tmp_path / f"{loader}.bin")
+        subprocess.check_call([BAL_QR, "--input", path, "--loader", loader, "--init-depth-threshold", str(threshold), "--dump-problem", out],
+                              stdout=subprocess.DEVNULL)
+        dumps[loader] = open(out, "rb").read()
+    assert dumps["parallel"] == dumps["map"]
+    cams, lms, off, oc, xy = _read_dump(str(tmp_path / "parallel.bin"))
+    assert np.array_equal(off, want_off) and np.array_equal(oc, got["obs_cam"]) and np.array_equal(xy, got["obs_xy"])
+    bp = rb.BalProblem.load_bal(path, np.float64, init_depth_threshold=threshold)
+    assert np.array_equal(bp.lm_off, off) and np.array_equal(bp.obs_cam, oc) and np.array_equal(bp.lms, lms) and np.array_equal(bp.cams, cams)
+
+
 def _load_ba_log(path):
     """ba_log.json as the reference's python/rootba/log.py reads it: top-level columns -> numpy arrays, `_static` nested"""
     d = json.load(open(path))
