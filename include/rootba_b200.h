@@ -170,6 +170,8 @@ int32_t rba_layout_selftest(const rba_problem_view* problem, int32_t rank, int32
  * flipped; observations of a landmark in ascending camera order like the reference's std::map, bal_problem.hpp:137;
  * duplicate observation / short or malformed file -> RBA_ERR_INVALID_ARGUMENT where the reference LOG(FATAL)s)
  * + normalize(scale) (:428-469, median-centre + MAD-scale, in double) when `normalize` != 0.
+ * A file whose name contains "bundle" is read as a Bundler "bundle.out" v0.3 file instead (load_bundler :284-404, chosen like
+ * autodetect_input_type :124-135; cameras with focal length 0 are dropped).
  * The file is parsed by `num_threads` threads (<= 0: all hardware threads) straight into the flat arrays of
  * rba_problem_view; the result is bit-identical to a one-fscanf-per-line loader (from_chars and "%lf" both round
  * correctly).  All values are double, as in the reference (cast to float happens after normalisation, :813-832). */

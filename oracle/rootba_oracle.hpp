@@ -1386,6 +1386,89 @@ inline int load_bal(const char* path, BalData& D) {
   return 0;
 }
 
+// Eigen::Quaternion(rotation matrix) as Sophus::SO3(R) uses it (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl:
+// trace branch / largest-diagonal branch).  R row-major; q = (x, y, z, w).  Restated, unpinned like the rest of Appendix A.
+inline void rot_to_quat(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t;
+    q[1] = (R[2] - R[6]) * t;
+    q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+}
+
+// ref: bal/bal_problem.cpp:284-404  load_bundler ("bundle.out" v0.3): one comment line, "num_cams num_points", per camera
+// 15 values (f k1 k2, R row-major, t; f == 0 = uninitialised camera: skipped, later cameras move up), per point position (3),
+// colour (3, ignored), view list: n, then n x (camera, feature key, x, y).  Same axis conventions as load_bal.
+inline int load_bundler(const char* path, BalData& D) {
+  FILE* f = std::fopen(path, "r");
+  if (!f) return -1;
+  char line[1000];
+  bool first = true, done = false;
+  while (!done && std::fgets(line, sizeof(line), f)) {  // readcommentline_or_throw (:76-107)
+    const size_t len = std::strlen(line);
+    if (len == 0 || (first && line[0] != '#')) { std::fclose(f); return -2; }
+    first = false;
+    done = line[len - 1] == '\n';
+  }
+  if (!done) { std::fclose(f); return -2; }
+  int ncf, nl;
+  if (std::fscanf(f, "%d %d", &ncf, &nl) != 2 || ncf <= 0 || nl <= 0) { std::fclose(f); return -2; }
+  std::vector<int> cam_map(ncf, -1);
+  D = BalData();
+  for (int i = 0; i < ncf; ++i) {
+    double p[15];
+    for (double& v : p) if (std::fscanf(f, "%lf", &v) != 1) { std::fclose(f); return -5; }
+    if (p[0] == 0) continue;
+    cam_map[i] = D.nc++;
+    double q[4], qn[4];
+    rot_to_quat(p + 3, q);
+    const double ai[4] = {1, 0, 0, 0};
+    quat_mul_sophus<double>(ai, q, qn);
+    const double c[10] = {qn[0], qn[1], qn[2], qn[3], p[12], -p[13], -p[14], p[0], p[1], p[2]};
+    D.cams.insert(D.cams.end(), c, c + 10);
+  }
+  D.nl = nl;
+  D.lms.resize((size_t)3 * nl);
+  D.lm_off.assign(1, 0);
+  struct O { int cam; double x, y; };
+  std::vector<O> v;
+  for (int l = 0; l < nl; ++l) {
+    double col[3];
+    int n;
+    for (int k = 0; k < 3; ++k) if (std::fscanf(f, "%lf", &D.lms[(size_t)3 * l + k]) != 1) { std::fclose(f); return -6; }
+    for (int k = 0; k < 3; ++k) if (std::fscanf(f, "%lf", &col[k]) != 1) { std::fclose(f); return -6; }
+    if (std::fscanf(f, "%d", &n) != 1) { std::fclose(f); return -6; }
+    v.clear();
+    for (int j = 0; j < n; ++j) {
+      int c, key; double x, y;
+      if (std::fscanf(f, "%d %d %lf %lf", &c, &key, &x, &y) != 4) { std::fclose(f); return -3; }
+      if (c >= 0 && c < ncf && cam_map[c] >= 0) v.push_back({cam_map[c], x, -y});
+    }
+    std::sort(v.begin(), v.end(), [](const O& a, const O& b) { return a.cam < b.cam; });
+    for (size_t i = 1; i < v.size(); ++i) if (v[i].cam == v[i - 1].cam) { std::fclose(f); return -7; }
+    for (auto& o : v) { D.obs_cam.push_back(o.cam); D.obs_xy.push_back(o.x); D.obs_xy.push_back(o.y); }
+    D.lm_off.push_back((int64_t)D.obs_cam.size());
+  }
+  std::fclose(f);
+  D.nobs = (int64_t)D.obs_cam.size();
+  return 0;
+}
+
 // ref: bal/bal_problem.cpp:428-469
 inline void normalize(BalData& D, double new_scale) {
   std::vector<double> tmp(D.nl);

@@ -111,7 +111,11 @@ int orc_max_threads() {
 // ---- BAL loader (double) ----
 int orc_bal_load(const char* path, int do_normalize, double scale, int* nc, int* nl, int64_t* nobs) {
   g_bal = BalData();
-  int rc = load_bal(path, g_bal);
+  // autodetect_input_type (bal_problem.cpp:124-135): "bundle" in the file name -> bundler format, else BAL
+  std::string name(path);
+  const size_t slash = name.find_last_of('/');
+  if (slash != std::string::npos) name = name.substr(slash + 1);
+  int rc = name.find("bundle") != std::string::npos ? load_bundler(path, g_bal) : load_bal(path, g_bal);
   if (rc != 0) return rc;
   if (do_normalize) normalize(g_bal, scale);
   *nc = g_bal.nc; *nl = g_bal.nl; *nobs = g_bal.nobs;

@@ -892,7 +892,8 @@ int32_t rba_bal_load(const char* path, int32_t normalize, double scale, int32_t 
   try {
     std::unique_ptr<rba_bal_file> f(new rba_bal_file());
     rootba_b200::LoadTimings t;
-    f->p = rootba_b200::load_bal_parallel(path, num_threads, &t);
+    if (rootba_b200::detail::is_bundler_file(path)) f->p = rootba_b200::load_bundler_soa(path, num_threads);  // autodetect_input_type
+    else f->p = rootba_b200::load_bal_parallel(path, num_threads, &t);
     const auto t0 = std::chrono::steady_clock::now();
     if (normalize) f->p.normalize(scale);
     f->timings[0] = t.read; f->timings[1] = t.count; f->timings[2] = t.parse; f->timings[3] = t.csr;

@@ -64,6 +64,37 @@ inline void quat_mul(const double* a, const double* b, double* r) {
   if (sq != 1.0) { const double s = 2.0 / (1.0 + sq); for (int i = 0; i < 4; ++i) r[i] *= s; }
 }
 
+// Eigen::Quaternion(rotation matrix) as Sophus::SO3(R) uses it: trace branch / largest-diagonal branch.
+// R row-major, q = (x, y, z, w).
+inline void rot_to_quat(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t;
+    q[1] = (R[2] - R[6]) * t;
+    q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+  }
+}
+
+// autodetect_input_type (bal_problem.cpp:124-135): "bundle" in the file name -> bundler, else BAL (.cereal is not supported)
+inline bool is_bundler_file(const std::string& path) {
+  const size_t slash = path.find_last_of('/');
+  return (slash == std::string::npos ? path : path.substr(slash + 1)).find("bundle") != std::string::npos;
+}
+
 // Whole file in memory, read with one pread stream per thread (parallel first touch; faster than faulting an mmap
 // in page by page from the parsing threads).
 struct FileBuffer {
@@ -374,11 +405,92 @@ inline BalProblemSoA<double> load_bal_parallel(const std::string& path, int nthr
   return out;
 }
 
+// ref: bal_problem.cpp:284-404  load_bundler ("bundle.out" v0.3).  View lists have variable length, so the token stream is
+// walked once, sequentially, over the in-memory file (these files are small next to the BAL "final" problems).
+inline BalProblemSoA<double> load_bundler_soa(const std::string& path, int nthreads = 0) {
+  using detail::is_ws;
+  const auto fail = [&](const char* why) -> void { throw std::runtime_error("Failed to parse '" + path + "' (" + why + ")"); };
+  if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+  detail::FileBuffer fb(path, nthreads);
+  const char* d = fb.data;
+  const size_t size = fb.size;
+  if (d[0] != '#') fail("expected a comment line");  // readcommentline_or_throw (:76-107)
+  size_t pos = 0;
+  while (pos < size && d[pos] != '\n') ++pos;
+  if (pos >= size) fail("expected a comment line");
+  ++pos;
+  const auto token = [&](const char*& a, const char*& b) {
+    while (pos < size && is_ws(d[pos])) ++pos;
+    if (pos >= size) fail("file ends early");
+    a = d + pos;
+    while (pos < size && !is_ws(d[pos])) ++pos;
+    b = d + pos;
+  };
+  const auto next_int = [&]() {
+    const char *a, *b;
+    token(a, b);
+    long long v = 0;
+    const auto r = std::from_chars(a, b, v);
+    if (r.ec != std::errc() || r.ptr != b) fail("bad integer");
+    return v;
+  };
+  const auto next_double = [&]() {
+    const char *a, *b;
+    token(a, b);
+    if (*a == '+') ++a;
+    double v = 0;
+    const auto r = std::from_chars(a, b, v);
+    if (r.ec != std::errc() || r.ptr != b) fail("bad number");
+    return v;
+  };
+  const long long ncf = next_int(), nlf = next_int();
+  if (ncf <= 0 || nlf <= 0 || ncf > INT32_MAX || nlf > INT32_MAX) fail("header");
+  BalProblemSoA<double> out;
+  std::vector<int> cam_map((size_t)ncf, -1);
+  for (long long i = 0; i < ncf; ++i) {
+    double p[15];
+    for (double& v : p) v = next_double();
+    if (p[0] == 0) continue;  // focal length 0: uninitialised camera (:323-326)
+    cam_map[(size_t)i] = out.nc++;
+    double q[4], qn[4];
+    detail::rot_to_quat(p + 3, q);
+    const double ai[4] = {1, 0, 0, 0};
+    detail::quat_mul(ai, q, qn);
+    const double c[10] = {qn[0], qn[1], qn[2], qn[3], p[12], -p[13], -p[14], p[0], p[1], p[2]};
+    out.cams.insert(out.cams.end(), c, c + 10);
+  }
+  out.nl = (int)nlf;
+  out.lms.resize((size_t)3 * nlf);
+  out.lm_off.assign(1, 0);
+  std::vector<std::pair<int32_t, std::array<double, 2>>> v;
+  for (long long l = 0; l < nlf; ++l) {
+    for (int k = 0; k < 3; ++k) out.lms[(size_t)(3 * l + k)] = next_double();
+    for (int k = 0; k < 3; ++k) (void)next_double();  // colour
+    const long long n = next_int();
+    v.clear();
+    for (long long j = 0; j < n; ++j) {
+      const long long c = next_int();
+      (void)next_int();  // feature key
+      const double x = next_double(), y = next_double();
+      if (c >= 0 && c < ncf && cam_map[(size_t)c] >= 0) v.push_back({cam_map[(size_t)c], {x, -y}});  // invert y axis (:390)
+    }
+    std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    for (size_t i = 0; i < v.size(); ++i) {
+      if (i > 0 && v[i].first == v[i - 1].first) fail("duplicate observation");  // CHECK(inserted) (:377)
+      out.obs_cam.push_back(v[i].first);
+      out.obs_xy.push_back(v[i].second[0]);
+      out.obs_xy.push_back(v[i].second[1]);
+    }
+    out.lm_off.push_back((int64_t)out.obs_cam.size());
+  }
+  return out;
+}
+
 // ref: bal_problem.cpp:773-852: load + normalise in double, then cast
 template <class Scalar>
 BalProblemSoA<Scalar> load_normalized_bal_problem_parallel(const std::string& path, bool normalize = true, double scale = 100.0,
                                                            int nthreads = 0, double init_depth_threshold = 0.0) {
-  BalProblemSoA<double> p = load_bal_parallel(path, nthreads);
+  BalProblemSoA<double> p = detail::is_bundler_file(path) ? load_bundler_soa(path, nthreads) : load_bal_parallel(path, nthreads);
   if (normalize) p.normalize(scale);
   p.filter_obs(init_depth_threshold);  // (the reference perturbs between the two, bal_problem.cpp:818-824; no perturbation here)
   return p.template copy_cast<Scalar>();

@@ -8,10 +8,13 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
+
+#include "bal_io_fast.hpp"  // detail::rot_to_quat, detail::is_bundler_file
 
 namespace rootba_b200 {
 
@@ -65,6 +68,60 @@ class BalProblem {
       for (double& v : p)
         if (std::fscanf(f, "%lf", &v) != 1) fail(f, path);
       landmarks_[i].p_w = {Scalar(p[0]), Scalar(p[1]), Scalar(p[2])};
+    }
+    std::fclose(f);
+  }
+
+  // ref: bal_problem.cpp:284-404, reference style: one fscanf per value, std::map per landmark
+  void load_bundler(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) throw std::runtime_error("Could not open '" + path + "'");
+    char line[1000];
+    bool first = true, done = false;
+    while (!done && std::fgets(line, sizeof(line), f)) {  // readcommentline_or_throw (:76-107)
+      const size_t len = std::strlen(line);
+      if (len == 0 || (first && line[0] != '#')) fail(f, path);
+      first = false;
+      done = line[len - 1] == '\n';
+    }
+    int ncf, nl;
+    if (!done || std::fscanf(f, "%d %d", &ncf, &nl) != 2 || ncf <= 0 || nl <= 0) fail(f, path);
+    cameras_.clear();
+    std::vector<int> cam_map(ncf, -1);
+    for (int i = 0; i < ncf; ++i) {
+      double p[15];
+      for (double& v : p)
+        if (std::fscanf(f, "%lf", &v) != 1) fail(f, path);
+      if (p[0] == 0) continue;  // focal length 0: uninitialised camera
+      cam_map[i] = (int)cameras_.size();
+      double q[4], qn[4];
+      detail::rot_to_quat(p + 3, q);
+      const double ai[4] = {1, 0, 0, 0};
+      quat_mul(ai, q, qn);
+      Camera c;
+      c.params = {Scalar(qn[0]), Scalar(qn[1]), Scalar(qn[2]), Scalar(qn[3]), Scalar(p[12]), Scalar(-p[13]), Scalar(-p[14]),
+                  Scalar(p[0]), Scalar(p[1]), Scalar(p[2])};
+      cameras_.push_back(c);
+    }
+    landmarks_.assign(nl, Landmark());
+    for (int l = 0; l < nl; ++l) {
+      double p[3], col[3];
+      int n;
+      for (double& v : p)
+        if (std::fscanf(f, "%lf", &v) != 1) fail(f, path);
+      for (double& v : col)
+        if (std::fscanf(f, "%lf", &v) != 1) fail(f, path);
+      if (std::fscanf(f, "%d", &n) != 1) fail(f, path);
+      landmarks_[l].p_w = {Scalar(p[0]), Scalar(p[1]), Scalar(p[2])};
+      for (int j = 0; j < n; ++j) {
+        int c, key;
+        double x, y;
+        if (std::fscanf(f, "%d %d %lf %lf", &c, &key, &x, &y) != 4) fail(f, path);
+        if (c < 0 || c >= ncf || cam_map[c] < 0) continue;
+        auto ins = landmarks_[l].obs.emplace(cam_map[c], Observation());
+        if (!ins.second) fail(f, path);
+        ins.first->second.pos = {Scalar(x), Scalar(-y)};
+      }
     }
     std::fclose(f);
   }
@@ -205,7 +262,8 @@ template <class Scalar>
 BalProblem<Scalar> load_normalized_bal_problem(const std::string& path, bool normalize = true, double scale = 100.0,
                                               double init_depth_threshold = 0.0) {
   BalProblem<double> p;
-  p.load_bal(path);
+  if (detail::is_bundler_file(path)) p.load_bundler(path);  // autodetect_input_type (bal_problem.cpp:124-135)
+  else p.load_bal(path);
   if (normalize) p.normalize(scale);
   p.filter_obs(init_depth_threshold);
   return p.template copy_cast<Scalar>();

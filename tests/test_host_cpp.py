@@ -187,6 +187,72 @@ def test_filter_obs_matches_oracle_and_numpy(tmp_path, threshold):
     assert np.array_equal(bp.lm_off, off) and np.array_equal(bp.obs_cam, oc) and np.array_equal(bp.lms, lms) and np.array_equal(bp.cams, cams)
 
 
+def _write_bundler(prob, path, rng, dead_cams):
+    """`prob` as a Bundler "bundle.out" v0.3 file (inverse of load_bundler, bal_problem.cpp:284-404): cameras listed in `dead_cams`
+    are written with focal length 0 (uninitialised) and still referenced by some view lists; views in random order."""
+    from rootba_b200.synthetic import quat_to_rot
+    flip = np.diag([1.0, -1.0, -1.0])
+    R = np.einsum("ij,mjk->mik", flip, quat_to_rot(prob.cams[:, :4]))
+    t = prob.cams[:, 4:7] @ flip.T
+    file_idx, lines = [], ["# Bundle file v0.3", None]
+    n_file = 0
+    for c in range(prob.nc):
+        while n_file in dead_cams:  # an uninitialised camera before camera c
+            lines += ["0 0 0", "0 0 0", "0 0 0", "0 0 0", "0 0 0"]
+            n_file += 1
+        file_idx.append(n_file)
+        lines.append(" ".join(f"{v:.17g}" for v in prob.cams[c, 7:10]))
+        lines += [" ".join(f"{v:.17g}" for v in R[c, r]) for r in range(3)]
+        lines.append(" ".join(f"{v:.17g}" for v in t[c]))
+        n_file += 1
+    lines[1] = f"{n_file} {prob.nl}"
+    for l in range(prob.nl):
+        lines.append(" ".join(f"{v:.17g}" for v in prob.lms[l]))
+        lines.append("255 0 0")
+        views = [(file_idx[int(prob.obs_cam[k])], k) for k in range(int(prob.lm_off[l]), int(prob.lm_off[l + 1]))]
+        order = rng.permutation(len(views))
+        items = [f"{views[i][0]} {7 * views[i][1]} {prob.obs_xy[views[i][1], 0]:.17g} {-prob.obs_xy[views[i][1], 1]:.17g}" for i in order]
+        if dead_cams and l % 3 == 0:
+            items.insert(0, f"{sorted(dead_cams)[0]} 1 0.5 0.5")  # a view of an uninitialised camera: must be ignored
+        lines.append(f"{len(items)} " + " ".join(items))
+    open(path, "w").write("\n".join(lines) + "\n")
+
+
+@pytest.mark.parametrize("dead_cams", [(), (0, 3)])
+def test_bundler_loader(tmp_path, dead_cams):
+    """Bundler "bundle.out" files (bal_problem.cpp:284-404; chosen by file name like autodetect_input_type :124-135): the three
+    loaders (SoA / C ABI, reference-style AoS, oracle) against the generator's arrays; uninitialised cameras are dropped and the
+    remaining ones renumbered; rotation via Eigen's matrix -> quaternion conversion."""
+    import rootba_b200 as rb
+    from oracle import oracle_py as orc
+    from rootba_b200.synthetic import synth_bal
+    _build()
+    prob = synth_bal(9, 120, 3.5, seed=12, normalize_scale=None)
+    path = str(tmp_path / "bundle.out")
+    _write_bundler(prob, path, np.random.default_rng(0), set(dead_cams))
+    dumps = {}
+    for loader in ("parallel", "map"):
+        out = str(tmp_path / f"{loader}.bin")
+        subprocess.check_call([BAL_QR, "--input", path, "--loader", loader, "--no-normalize", "--dump-problem", out], stdout=subprocess.DEVNULL)
+        dumps[loader] = open(out, "rb").read()
+    assert dumps["parallel"] == dumps["map"]
+    cams, lms, off, oc, xy = _read_dump(str(tmp_path / "parallel.bin"))
+    assert np.array_equal(off, prob.lm_off) and np.array_equal(oc, prob.obs_cam)  # dead cameras gone, indices compacted
+    assert np.array_equal(xy, prob.obs_xy) and np.array_equal(lms, prob.lms)      # %.17g round trip: exact
+    q_sign = np.sign(np.sum(cams[:, :4] * prob.cams[:, :4], axis=1, keepdims=True))
+    assert np.allclose(cams[:, :4] * q_sign, prob.cams[:, :4], atol=1e-14) and np.allclose(cams[:, 4:], prob.cams[:, 4:], rtol=1e-15, atol=1e-15)
+    ref = orc.load_bal(path, normalize=False)
+    assert np.array_equal(ref["lm_off"], off) and np.array_equal(ref["obs_cam"], oc) and np.array_equal(ref["obs_xy"], xy)
+    assert rel_err(ref["cams"], cams) < 1e-15 and np.array_equal(ref["lms"], lms)
+    bp = rb.BalProblem.load_bal(path, np.float64, normalize=True)   # C ABI, with normalisation
+    refn = orc.load_bal(path, normalize=True)
+    assert np.array_equal(bp.lm_off, off) and rel_err(bp.cams, refn["cams"]) < 1e-14 and rel_err(bp.lms, refn["lms"]) < 1e-14
+    bad = tmp_path / "bundle_bad.out"
+    bad.write_text("no comment line\n1 1\n")
+    for loader in ("parallel", "map"):
+        assert subprocess.run([BAL_QR, "--input", str(bad), "--loader", loader, "--dump-problem", str(tmp_path / "x.bin")], capture_output=True).returncode != 0
+
+
 def _load_ba_log(path):
     """ba_log.json as the reference's python/rootba/log.py reads it: top-level columns -> numpy arrays, `_static` nested"""
     d = json.load(open(path))
