@@ -31,6 +31,8 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "ms/LM-iter", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert len(d["cg_iterations"]) == 2
+    one = d["cpu_baseline_1thread"]  # T = all cores and T = 1
+    assert one["cores"] == 1 and one["value"] > 0 and one["unit"] == "ms/LM-iter"
 
 
 def test_reference_arm_other_ranks_stay_silent():
