@@ -82,7 +82,12 @@ typedef struct {
                                               Jp^T Jp x - (Q1d^T Jp)^T (Q1d^T Jp) x from the per-observation records
                                               (same result up to rounding, ~n/2.7 x fewer bytes, but the subtraction gives
                                               up the float32 robustness of the square-root form: recommended with f64) */
-  int32_t reserved[5];
+  int32_t stage2_form;                     /* gradient b and SCHUR_JACOBI blocks of the reduced system: 0 = from the stored Q2 panels
+                                              like the reference (ipp:443-466, :520-552: sums of squares, no cancellation;
+                                              default), 1 = through the orthogonality identities Jp^T r - Q1d^T (Q1^T r)_d and
+                                              Jp^T Jp - Q1d^T Q1d (O(n) per landmark, but they cancel: float64 only).  With
+                                              operator_form = 1 no panels exist and form 1 is used. */
+  int32_t reserved[4];
 } rba_solver_opts;
 
 /* ResidualInfo (bal/residual_info.hpp:59-89) */

@@ -37,7 +37,7 @@ class SolverOpts(C.Structure):
                 ("max_linear_solver_iterations", C.c_int32), ("eta", C.c_double),
                 ("residual_reset_period", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32), ("pcg_check_period", C.c_int32), ("use_cuda_graphs", C.c_int32),
-                ("operator_form", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("operator_form", C.c_int32), ("stage2_form", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class ResidualInfo(C.Structure):
@@ -79,9 +79,9 @@ def struct_to_dict(s: C.Structure) -> dict:
 def build(force: bool = False) -> str:
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     src_dir = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in ("solver.cu", "kernels.cuh", "layout.hpp", "nccl_dyn.hpp")] + [HEADER_PATH]
-    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
-        subprocess.check_call(["make", "-C", src_dir, "-s"])
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.check_call(["make", "-C", src_dir, "-s"])  # make knows every dependency (kernels, layout, host loaders, header)
     return LIB_PATH
 
 

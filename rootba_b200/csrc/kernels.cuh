@@ -74,10 +74,15 @@ struct DevPtrs {
   S* jl;         // [nslots][6]  scaled Jl (2x3)
   S* res;        // [nslots][2]  weighted residual
   S* lmk;        // [nsorted][24] Ru(6) q1r_u(3) Rd(6) q1r_d(3) Jl_col_scale(3) pad
+  S* qtr;        // [nslots][2]  Q^T r of the landmark the slot belongs to: row rho of landmark (slot0) at qtr[2 slot0 + rho]
+  S* dmp;        // [nslots][28] the 3 damping rows of the Q2 panel restricted to the 9 columns of the slot (3x9) + 1 pad
+  S* blk0;       // [nslots][48] lambda-independent part of the slot's SCHUR_JACOBI block (45 upper entries) -- stage-1 scratch
   // camera vectors [9 nc]
   S* diag2; S* scaling; S* b; S* x; S* r; S* z; S* p; S* q; S* y; S* inc;
   S* blocks;     // [nc][81] preconditioner blocks (damping added)
   S* jblocks;    // [nc][81] JACOBI blocks (scaled, no damping)
+  S* blocks0;    // [nc][81] lambda-independent part of the SCHUR_JACOBI blocks (rows 3..2n-1 of the Q2 panels; this shard)
+  S* b0;         // [9 nc]   lambda-independent part of the gradient (this shard)
   S* inv;        // [nc][81] explicit inverses
   // scatter buffers
   S* yobs;       // [nyslots][9]
@@ -740,6 +745,9 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
       lk[6] = A_AT(0, 3); lk[7] = A_AT(1, 3); lk[8] = A_AT(2, 3);
       lk[18] = jls[0]; lk[19] = jls[1]; lk[20] = jls[2];
     }
+    // Q^T r (rows 0..2 = Q1^T r, rows 3..2n-1 = Q2^T r: the residual column of the marginalised block, ipp:443-466)
+    if (active)
+      for (int rho = j; rho < nrows; rho += G) D.qtr[2 * (size_t)slot0 + rho] = A_AT(rho, 3);
     // ---- d. apply Q^T = H2 H1 H0 to the block-diagonal Jp (compact WY) and write q1u + panel ----
     V2* ptile = reinterpret_cast<V2*>(D.panel + T.panel_off);
     const int ncols = 9 * n;
@@ -894,13 +902,19 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
 __host__ __device__ inline int stage2_need(int n, int G, int KP) {
   const int W = 32 / G, Wn = W * n;
   const int CS = (2 * G * KP) | 1;
-  return 3 * W * CS + Wn * 9 + W * 16 + 8;
+  return 3 * W * CS + Wn * 9 + W * 20 + 8;
 }
 
 // One warp per tile, one lane per observation: the 112-byte q1u / q1d and 80-byte jp records are moved with
 // 16-byte vector accesses straight from / to registers; only the 3 damping rows (which must land in the
 // column-interleaved panel layout) and the gradient are staged through shared memory for coalesced stores.
-template <class S>
+// PANEL = true (default, the reference's arithmetic): the gradient is P^T (Q2^T r) (ipp:443-466) and the SCHUR_JACOBI
+// blocks are B^T B of the panel columns (ipp:520-552).  Panel rows 3..2n-1 do not depend on lambda, so their
+// contribution (b0, blocks0) is accumulated once per linearisation by k_panel_grad_blocks; this kernel adds the part of
+// the three damping rows: yobs[slot] = sum_d D_d (Q^T r)_{damping row d}, and keeps the rows' 3x9 entries per slot (dmp)
+// for the block kernel.  PANEL = false (no panels stored: operator_form = implicit): the orthogonality identities
+//   P^T (Q2^T r) = Jp^T r - Q1d^T (Q1^T r)_d ,  B^T B = Jp^T Jp - Q1d^T Q1d   (they cancel: float64 recommended).
+template <class S, bool PANEL>
 __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<S> sc, int write_panel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using V2 = typename ST<S>::V2;
@@ -916,14 +930,14 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
     S* ws = scratch_ptr(sc, ws_smem, stage2_need(n, G, KP));
     S* sD = ws;                      // [3][W][CS] damping rows in (landmark, column) order
     S* sG = sD + 3 * W * CS;         // [Wn][9]    gradient contribution per observation
-    S* sRot = sG + Wn * 9;           // [W][16]    6 rotations (c,s) + damped Q1^T r (3)
+    S* sRot = sG + Wn * 9;           // [W][20]    6 rotations (c,s) + damped Q1^T r (3) + residual entries of the damping rows (3)
     // ---- rotations of landmark `lane` (ref: ipp:188-209), Eigen makeGivens / applyOnTheLeft ----
     if (lane < T.nvalid) {
       S* lk = D.lmk + 24 * (size_t)(T.lm_base + lane);
       S Rw[3][3] = {{lk[0], lk[1], lk[2]}, {0, lk[3], lk[4]}, {0, 0, lk[5]}};
       S Dw[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
       S rr[3] = {lk[6], lk[7], lk[8]}, dr[3] = {0, 0, 0};
-      S* ro = sRot + 16 * lane;
+      S* ro = sRot + 20 * lane;
       if (lambda == S(0)) {
 #pragma unroll
         for (int q = 0; q < 6; ++q) { ro[2 * q] = 1; ro[2 * q + 1] = 0; }
@@ -945,6 +959,7 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
           }
       }
       ro[12] = rr[0]; ro[13] = rr[1]; ro[14] = rr[2];
+      ro[15] = dr[0]; ro[16] = dr[1]; ro[17] = dr[2];
       lk[9] = Rw[0][0]; lk[10] = Rw[0][1]; lk[11] = Rw[0][2]; lk[12] = Rw[1][1]; lk[13] = Rw[1][2]; lk[14] = Rw[2][2];
       lk[15] = rr[0]; lk[16] = rr[1]; lk[17] = rr[2];
     }
@@ -952,16 +967,20 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
     // ---- one observation per lane and step: q1d, damping-row entries, gradient ----
     if (active) {
       Rot<S> rot[6];
-      const S* ro = sRot + 16 * g;
+      const S* ro = sRot + 20 * g;
 #pragma unroll
       for (int q = 0; q < 6; ++q) { rot[q].c = ro[2 * q]; rot[q].s = ro[2 * q + 1]; }
       const S rr0 = ro[12], rr1 = ro[13], rr2 = ro[14];
+      const S dr0 = ro[15], dr1 = ro[16], dr2 = ro[17];
       for (int i = j; i < n; i += G) {
         const size_t sl = (size_t)(T.slot_base + g * n + i);
-        S q[28], jp[20];
+        S q[28], jp[PANEL ? 4 : 20], dm[PANEL ? 28 : 4];
         load_rec<S, 28>(D.q1u + 28 * sl, q);
-        load_rec<S, 20>(D.jp + 20 * sl, jp);
-        const S r0 = D.res[2 * sl], r1 = D.res[2 * sl + 1];
+        S r0 = 0, r1 = 0;
+        if constexpr (!PANEL) {
+          load_rec<S, 20>(D.jp + 20 * sl, jp);
+          r0 = D.res[2 * sl]; r1 = D.res[2 * sl + 1];
+        }
         S* d0 = sD + (0 * W + g) * CS + 9 * i;
         S* d1 = sD + (1 * W + g) * CS + 9 * i;
         S* d2 = sD + (2 * W + g) * CS + 9 * i;
@@ -976,11 +995,21 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
             for (int m = 0; m <= nn; ++m) rot_apply(rot[qi++], dv[nn - m], qv[nn]);
           q[p] = qv[0]; q[9 + p] = qv[1]; q[18 + p] = qv[2];
           d0[p] = dv[0]; d1[p] = dv[1]; d2[p] = dv[2];
-          // gradient of the reduced system: b_c = jp_c^T r_i - q1d_c^T (Q1^T r)_d
-          go[p] = jp[p] * r0 + jp[9 + p] * r1 - (qv[0] * rr0 + qv[1] * rr1 + qv[2] * rr2);
+          if constexpr (PANEL) {
+            // damping-row part of P^T (Q2^T r) (ipp:443-466); rows 3..2n-1 are in b0
+            dm[p] = dv[0]; dm[9 + p] = dv[1]; dm[18 + p] = dv[2];
+            go[p] = dv[0] * dr0 + dv[1] * dr1 + dv[2] * dr2;
+          } else {
+            // gradient of the reduced system: b_c = jp_c^T r_i - q1d_c^T (Q1^T r)_d
+            go[p] = jp[p] * r0 + jp[9 + p] * r1 - (qv[0] * rr0 + qv[1] * rr1 + qv[2] * rr2);
+          }
         }
         q[27] = 0;
         store_rec<S, 28>(D.q1d + 28 * sl, q);
+        if constexpr (PANEL) {
+          dm[27] = 0;
+          store_rec<S, 28>(D.dmp + 28 * sl, dm);
+        }
       }
     }
     __syncwarp();
@@ -1072,10 +1101,14 @@ __global__ void __launch_bounds__(128) k_matvec_implicit(DevPtrs<S> D, int tile_
 //   thread per ReduceItem chunk of <= 32 observations ... here: one thread per (item, 8-slot subchunk) would
 //   be finer; we use thread per item-of-32 built on the host (pb_items).
 // ------------------------------------------------------------------------------------------------
-template <class S>
-__global__ void __launch_bounds__(128) k_precond_partial(const S* __restrict__ jp, const S* __restrict__ q1d,
+// MODE 0: JACOBI  sum Jp_i^T Jp_i                                         (ipp:554-569)
+// MODE 1: SCHUR_JACOBI through the orthogonality identity  Jp^T Jp - Q1d^T Q1d  (operator_form = implicit only)
+// MODE 2: SCHUR_JACOBI, part of the 3 damping rows  sum_d D_d^T D_d  from the dmp records   (ipp:520-552, rows 2n..2n+2)
+// MODE 3: SCHUR_JACOBI, lambda-independent part: sum of the per-slot blk0 records written by k_panel_grad_blocks
+template <class S, int MODE>
+__global__ void __launch_bounds__(128) k_precond_partial(const S* __restrict__ recA, const S* __restrict__ recB,
                                                           const int* __restrict__ slots, const ReduceItem* __restrict__ items,
-                                                          int nitems, int schur, S* __restrict__ pblk) {
+                                                          int nitems, S* __restrict__ pblk) {
   const int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= nitems) return;
   const ReduceItem I = items[it];
@@ -1084,42 +1117,43 @@ __global__ void __launch_bounds__(128) k_precond_partial(const S* __restrict__ j
   for (int k = 0; k < 45; ++k) acc[k] = 0;
   for (int e = I.begin; e < I.end; ++e) {
     const size_t sl = (size_t)slots[e];
-    S v[48];
-    if (sizeof(S) == 4) {
-      const float4* a4 = reinterpret_cast<const float4*>(jp + 20 * sl);
-      const float4* b4 = reinterpret_cast<const float4*>(q1d + 28 * sl);
+    if constexpr (MODE == 3) {
+      S v[48];
+      load_rec<S, 48>(recA + 48 * sl, v);
 #pragma unroll
-      for (int q = 0; q < 5; ++q) { const float4 t = __ldg(a4 + q); v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+      for (int k = 0; k < 45; ++k) acc[k] += v[k];
+    } else if constexpr (MODE == 2) {
+      S v[28];
+      load_rec<S, 28>(recA + 28 * sl, v);
+      int k = 0;
 #pragma unroll
-      for (int q = 0; q < 7; ++q) { const float4 t = __ldg(b4 + q); v[20 + 4 * q] = t.x; v[21 + 4 * q] = t.y; v[22 + 4 * q] = t.z; v[23 + 4 * q] = t.w; }
+      for (int a = 0; a < 9; ++a)
+#pragma unroll
+        for (int b = a; b < 9; ++b) acc[k++] += v[a] * v[b] + v[9 + a] * v[9 + b] + v[18 + a] * v[18 + b];
     } else {
-      const double2* a2 = reinterpret_cast<const double2*>(jp + 20 * sl);
-      const double2* b2 = reinterpret_cast<const double2*>(q1d + 28 * sl);
+      S v[20], w[MODE == 1 ? 28 : 4];
+      load_rec<S, 20>(recA + 20 * sl, v);
+      if constexpr (MODE == 1) load_rec<S, 28>(recB + 28 * sl, w);
+      int k = 0;
 #pragma unroll
-      for (int q = 0; q < 10; ++q) { const double2 t = __ldg(a2 + q); v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+      for (int a = 0; a < 9; ++a)
 #pragma unroll
-      for (int q = 0; q < 14; ++q) { const double2 t = __ldg(b2 + q); v[20 + 2 * q] = t.x; v[21 + 2 * q] = t.y; }
+        for (int b = a; b < 9; ++b) {
+          S sacc = v[a] * v[b] + v[9 + a] * v[9 + b];
+          if constexpr (MODE == 1) sacc -= w[a] * w[b] + w[9 + a] * w[9 + b] + w[18 + a] * w[18 + b];
+          acc[k++] += sacc;
+        }
     }
-    // v[0..17] = jp rows, v[20..46] = q1d rows
-    int k = 0;
-#pragma unroll
-    for (int a = 0; a < 9; ++a)
-#pragma unroll
-      for (int b = a; b < 9; ++b) {
-        S sacc = v[a] * v[b] + v[9 + a] * v[9 + b];
-        if (schur) sacc -= v[20 + a] * v[20 + b] + v[29 + a] * v[29 + b] + v[38 + a] * v[38 + b];
-        acc[k++] += sacc;
-      }
   }
   S* o = pblk + 48 * (size_t)it;
 #pragma unroll
   for (int k = 0; k < 45; ++k) o[k] = acc[k];
 }
 
-// blocks[cam][81] = sum of partial upper triangles (symmetrised)
+// blocks[cam][81] = (addend[cam][81] +) sum of partial upper triangles (symmetrised)
 template <class S>
 __global__ void k_precond_final(const S* __restrict__ pblk, const int* __restrict__ cam_item_ptr, int nc,
-                                S* __restrict__ blocks) {
+                                const S* __restrict__ addend, S* __restrict__ blocks) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 45 * nc) return;
   const int cam = i / 45, k = i - 45 * cam;
@@ -1128,8 +1162,82 @@ __global__ void k_precond_final(const S* __restrict__ pblk, const int* __restric
   int a = 0, rem = k;
   while (rem >= 9 - a) { rem -= 9 - a; ++a; }
   const int b = a + rem;
+  if (addend) s += addend[81 * (size_t)cam + 9 * a + b];
   blocks[81 * (size_t)cam + 9 * a + b] = s;
   blocks[81 * (size_t)cam + 9 * b + a] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2p  lambda-independent part of the RCS gradient and of the SCHUR_JACOBI blocks from the stored Q2 panels, once per
+//      linearisation:  per observation slot i of a landmark, with B = panel rows 3..2n-1 restricted to the slot's 9 columns
+//      and t = (Q2^T r) rows 3..2n-1:   blk0[slot] = B^T B (45 upper entries),   yobs[slot] = B^T t.
+//   ref: ipp:520-552 (add_Q2TJp_T_Q2TJp_blockdiag), ipp:443-466 (add_Q2TJp_T_Q2Tr).  Sums of squares: no cancellation,
+//   positive semi-definite by construction -- the float32 robustness the square-root formulation is about.
+//   Warp per tile, lane per observation (32 observations per pass); a row of the tile is covered exactly once by the
+//   lanes' 5 two-scalar loads each (L1 merges the sectors shared by neighbouring observations).
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(128) k_panel_grad_blocks(DevPtrs<S> D, int want_blocks) {
+  using V2 = typename ST<S>::V2;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+    const TileInfo T = D.tiles[t];
+    const int n = T.n, G = T.G, KP = T.KP;
+    const int lg = 31 - __clz(G);
+    const int nobs = T.nvalid * n;
+    const int nrows = 2 * n - 3;
+    const V2* __restrict__ ptile = reinterpret_cast<const V2*>(D.panel + T.panel_off);
+    const size_t rstride = (size_t)KP * 32;
+    for (int e = lane; e < nobs; e += 32) {
+      const int g = e / n, i = e - g * n;
+      const int c0 = 9 * i;
+      const bool odd = c0 & 1;
+      const int p0 = c0 >> 1;
+      int off[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int p = p0 + q;
+        off[q] = (p >> lg) * 32 + g * G + (p & (G - 1));
+      }
+      const S* __restrict__ tq = D.qtr + 2 * (size_t)(T.slot_base + g * n) + 3;
+      S acc[45], gacc[9];
+#pragma unroll
+      for (int k = 0; k < 45; ++k) acc[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) gacc[k] = 0;
+#pragma unroll 2
+      for (int r = 0; r < nrows; ++r) {
+        const V2* pr = ptile + (size_t)r * rstride;
+        V2 a[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) a[q] = __ldg(pr + off[q]);
+        const S tr = __ldg(tq + r);
+        const S el[10] = {a[0].x, a[0].y, a[1].x, a[1].y, a[2].x, a[2].y, a[3].x, a[3].y, a[4].x, a[4].y};
+        S v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[k] = odd ? el[k + 1] : el[k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gacc[k] += v[k] * tr;
+        if (want_blocks) {
+          int k = 0;
+#pragma unroll
+          for (int x = 0; x < 9; ++x)
+#pragma unroll
+            for (int y = x; y < 9; ++y) acc[k++] += v[x] * v[y];
+        }
+      }
+      const size_t sl = (size_t)(T.slot_base + e);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) D.yobs[9 * sl + k] = gacc[k];
+      if (want_blocks) {
+        S o[48];
+#pragma unroll
+        for (int k = 0; k < 45; ++k) o[k] = acc[k];
+        o[45] = o[46] = o[47] = 0;
+        store_rec<S, 48>(D.blk0 + 48 * sl, o);
+      }
+    }
+  }
 }
 
 // K3b  (blocks + lambda I) -> explicit inverse via Cholesky (ref: cg/preconditioner.hpp:79-120; pose damping
@@ -1823,13 +1931,14 @@ __global__ void __launch_bounds__(128) k_pcg_q(DevPtrs<S> D, const PcgState* st,
 // y_local = sum of camera partials (multi-GPU: feeds the all-reduce)
 template <class S>
 __global__ void k_cam_final9(const S* __restrict__ partial, const int* __restrict__ cam_item_ptr, int nc,
-                             S* __restrict__ out, const int* done) {
+                             S* __restrict__ out, const int* done, const S* __restrict__ addend = nullptr) {
   if (done && *done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * nc) return;
   const int cam = i / 9, c = i - 9 * cam;
   S s = 0;
   for (int it = cam_item_ptr[cam]; it < cam_item_ptr[cam + 1]; ++it) s += partial[9 * (size_t)it + c];
+  if (addend) s += addend[i];
   out[i] = s;
 }
 

@@ -97,6 +97,7 @@ struct Solver : rba_handle {
   // observation and row chunk) or the observation CSR of the implicit form
   const int* op_slots = nullptr; const ReduceItem* op_items = nullptr; const int* op_item_ptr = nullptr; int n_op_items = 0;
   bool implicit_op = false;
+  bool panel_form = true;        // gradient and SCHUR_JACOBI blocks from the Q2 panels (reference form) instead of the identities
   int imp_tile_split = 0;        // tiles [0, split) have <= IMP_MAXSLOTS slots and take the streamed kernel
   size_t imp_smem = 0; int imp_grid = 1;
   ReduceItem* d_pb_items = nullptr; int* d_pb_item_ptr = nullptr; int n_pb_items = 0;
@@ -239,6 +240,9 @@ struct Solver : rba_handle {
     }
     implicit_op = opt.operator_form == 1;
     if (opt.operator_form != 0 && opt.operator_form != 1) { g_err = "operator_form must be 0 (dense) or 1 (implicit)"; return RBA_ERR_INVALID_ARGUMENT; }
+    if (opt.stage2_form != 0 && opt.stage2_form != 1) { g_err = "stage2_form must be 0 (Q2 panel, reference) or 1 (orthogonality identity)"; return RBA_ERR_INVALID_ARGUMENT; }
+    // gradient / SCHUR_JACOBI blocks from the stored Q2 panels like the reference, unless there are no panels (implicit operator)
+    panel_form = !implicit_op && opt.stage2_form == 0;
     if (implicit_op) {
       while (imp_tile_split < (int)L.tiles.size() && (32 / L.tiles[imp_tile_split].G) * L.tiles[imp_tile_split].n <= IMP_MAXSLOTS) ++imp_tile_split;
       imp_smem = (size_t)IMP_WARPS * IMP_NS * (size_t)IMP_MAXSLOTS * 48 * sizeof(S);
@@ -263,6 +267,13 @@ struct Solver : rba_handle {
     TRY(dalloc(&D.jl, (size_t)6 * L.nslots));
     TRY(dalloc(&D.res, (size_t)2 * L.nslots));
     TRY(dalloc(&D.lmk, (size_t)24 * L.sorted_lm.size()));
+    TRY(dalloc(&D.qtr, (size_t)2 * L.nslots));
+    if (panel_form) {
+      TRY(dalloc(&D.dmp, (size_t)28 * L.nslots));
+      if (opt.preconditioner_type == 1) TRY(dalloc(&D.blk0, (size_t)48 * L.nslots));
+      TRY(dalloc(&D.blocks0, (size_t)81 * nc));
+      TRY(dalloc(&D.b0, (size_t)9 * nc));
+    }
     for (S** v : {&D.diag2, &D.scaling, &D.b, &D.x, &D.r, &D.z, &D.p, &D.q, &D.y, &D.inc}) TRY(dalloc(v, (size_t)9 * nc));
     TRY(dalloc(&D.blocks, (size_t)81 * nc)); TRY(dalloc(&D.jblocks, (size_t)81 * nc)); TRY(dalloc(&D.inv, (size_t)81 * nc));
     TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
@@ -304,7 +315,8 @@ struct Solver : rba_handle {
       TRY(setup(k2_sc, K2_CAP, need2, k2_smem, k2_bps, k2_max_blocks));
       CU(cudaFuncSetAttribute((k_linearize_qr<S, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
       CU(cudaFuncSetAttribute((k_linearize_qr<S, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
-      CU(cudaFuncSetAttribute(k_stage2<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
+      CU(cudaFuncSetAttribute((k_stage2<S, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
+      CU(cudaFuncSetAttribute((k_stage2<S, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
     }
     k4_smem_small = (size_t)K4_WARPS * L.k4_scratch_per_warp * sizeof(S);
     if (k4_smem_small > 200 * 1024) { g_err = "matvec scratch exceeds shared memory"; return RBA_ERR_UNSUPPORTED; }
@@ -355,7 +367,7 @@ struct Solver : rba_handle {
   static constexpr int K4_STAGE = RBA_K4_STAGE;  // bytes per stage (2 rows of an f32 KP=9 tile)
   static constexpr int TILE_WARPS = 4;
   static constexpr int K1_CAP = 3904;   // scalars of shared memory per warp: linearize+QR needs 60 * W * n + 64 (= 3904 for the standard tiles)
-  static constexpr int K2_CAP = 2944;   // stage 2 needs 3 * W * CS + 9 * W * n + 16 W + 8 (<= 2944 for the standard tiles)
+  static constexpr int K2_CAP = 3072;   // stage 2 needs 3 * W * CS + 9 * W * n + 20 W + 8 (<= 3048 for the standard tiles)
   Scratch<S> k1_sc{}, k2_sc{};
   size_t k1_smem = 0, k2_smem = 0;
   int k1_bps = 2, k2_bps = 2, k1_max_blocks = 296, k2_max_blocks = 296;
@@ -472,11 +484,12 @@ struct Solver : rba_handle {
   }
 
   // deterministic per-camera sum of yobs[slot][9] over a CSR -> dst[9 nc] (+ all-reduce across shards)
-  int camera_reduce(const int* slots, const ReduceItem* items, int nitems, const int* item_ptr, S* dst, const int* done) {
+  int camera_reduce(const int* slots, const ReduceItem* items, int nitems, const int* item_ptr, S* dst, const int* done,
+                    const S* addend = nullptr, bool reduce_ranks = true) {
     k_cam_reduce<S><<<grid_for(nitems, 8, 8), 256, 0, stream>>>(D.yobs, slots, items, nitems, D.partial, done);
-    k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, item_ptr, nc, dst, done);
+    k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, item_ptr, nc, dst, done, addend);
     launches += 2;
-    return allreduce(dst, (size_t)9 * nc, false);
+    return reduce_ranks ? allreduce(dst, (size_t)9 * nc, false) : RBA_OK;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -519,7 +532,17 @@ struct Solver : rba_handle {
     launches += 2;
     if (opt.preconditioner_type == 0) {
       // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)
-      rc = precond_blocks(false, D.jblocks); if (rc) return rc;
+      rc = precond_blocks(0, D.jblocks, nullptr, true); if (rc) return rc;
+    }
+    if (panel_form) {
+      // rows 3..2n-1 of the Q2 panels do not change with lambda: their part of the gradient (ipp:443-466) and of the
+      // SCHUR_JACOBI blocks (ipp:520-552) is accumulated once per linearisation (this shard only; the sum over the
+      // shards happens in solve() together with the damping-row part)
+      const int want_blocks = opt.preconditioner_type == 1 ? 1 : 0;
+      k_panel_grad_blocks<S><<<tile_grid(sm_count * 8), TILE_WARPS * 32, 0, stream>>>(D, want_blocks);
+      ++launches;
+      rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b0, nullptr, nullptr, false); if (rc) return rc;
+      if (want_blocks) { rc = precond_blocks(3, D.blocks0, nullptr, false); if (rc) return rc; }
     }
     rc = allreduce_flags(); if (rc) return rc;
     CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -536,11 +559,18 @@ struct Solver : rba_handle {
     return RBA_OK;
   }
 
-  int precond_blocks(bool schur, S* dst) {
-    k_precond_partial<S><<<(n_pb_items + 127) / 128, 128, 0, stream>>>(D.jp, D.q1d, d_csr_obs_slots, d_pb_items, n_pb_items, schur ? 1 : 0, D.pblk);
-    k_precond_final<S><<<(45 * nc + 255) / 256, 256, 0, stream>>>(D.pblk, d_pb_item_ptr, nc, dst);
+  // per-camera 9x9 blocks: deterministic two-phase sum over the camera-major observation CSR (modes: see k_precond_partial)
+  int precond_blocks(int mode, S* dst, const S* addend, bool reduce_ranks) {
+    const int g = (n_pb_items + 127) / 128;
+    switch (mode) {
+      case 0: k_precond_partial<S, 0><<<g, 128, 0, stream>>>(D.jp, (const S*)nullptr, d_csr_obs_slots, d_pb_items, n_pb_items, D.pblk); break;
+      case 1: k_precond_partial<S, 1><<<g, 128, 0, stream>>>(D.jp, D.q1d, d_csr_obs_slots, d_pb_items, n_pb_items, D.pblk); break;
+      case 2: k_precond_partial<S, 2><<<g, 128, 0, stream>>>(D.dmp, (const S*)nullptr, d_csr_obs_slots, d_pb_items, n_pb_items, D.pblk); break;
+      default: k_precond_partial<S, 3><<<g, 128, 0, stream>>>(D.blk0, (const S*)nullptr, d_csr_obs_slots, d_pb_items, n_pb_items, D.pblk); break;
+    }
+    k_precond_final<S><<<(45 * nc + 255) / 256, 256, 0, stream>>>(D.pblk, d_pb_item_ptr, nc, addend, dst);
     launches += 2;
-    return allreduce(dst, (size_t)81 * nc, false);
+    return reduce_ranks ? allreduce(dst, (size_t)81 * nc, false) : RBA_OK;
   }
 
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
@@ -591,6 +621,9 @@ struct Solver : rba_handle {
     const bool fused = opt.nranks > 1 && peer_ok;
     if (fused) ++ar_seq;
     S* ydst = fused ? ybuf + (size_t)(ar_seq & 1) * 9 * nc : D.y;
+    // k_cam_reduce_final writes y only for cameras that have observations in this shard; D.y is all-reduced IN PLACE, so
+    // without this the other cameras would carry the previous iteration's global sum into the next all-reduce
+    if (opt.nranks > 1 && !fused) CU(cudaMemsetAsync(D.y, 0, (size_t)9 * nc * sizeof(S), stream));
     int rc = launch_ex(k_cam_reduce_final<S>, grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
                        op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, ydst, (const int*)&d_state->done, (int)use_pdl);
     if (rc) return rc;
@@ -621,11 +654,12 @@ struct Solver : rba_handle {
     tm.matvec_launches = 0;
     int rc = start(ev_stage2); if (rc) return rc;
     // stage 2: landmark damping + gradient (+ SCHUR_JACOBI blocks)
-    k_stage2<S><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc, ko.write_panel);
+    if (panel_form) k_stage2<S, true><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc, ko.write_panel);
+    else k_stage2<S, false><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc, ko.write_panel);
     ++launches;
-    rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b, nullptr); if (rc) return rc;
+    rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b, nullptr, panel_form ? D.b0 : nullptr); if (rc) return rc;
     const bool schur = opt.preconditioner_type == 1;
-    if (schur) { rc = precond_blocks(true, D.blocks); if (rc) return rc; }
+    if (schur) { rc = panel_form ? precond_blocks(2, D.blocks, D.blocks0, true) : precond_blocks(1, D.blocks, nullptr, true); if (rc) return rc; }
     rc = stop(ev_stage2); if (rc) return rc;
     rc = start(ev_precond); if (rc) return rc;
     // pose damping lambda*I added to the blocks, then explicit inverse (ref: linearization_qr.hpp:796-802, linearizor_qr.cpp:228-237)
@@ -686,6 +720,7 @@ struct Solver : rba_handle {
       cg->reason = h_state[0].reason;
       cg->num_matvecs = h_state[0].iter + h_state[0].iter / period;
     }
+    if (h_state[0].reason == 99) g_err = "PCG: a peer rank did not publish its operator output in time (peer-memory all-reduce timed out)";
     return RBA_OK;
   }
 

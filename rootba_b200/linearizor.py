@@ -58,6 +58,7 @@ class SolverOptions:  # bal/solver_options.hpp (QR-relevant subset, reference de
     nranks: int = 1
     pcg_check_period: int = 4
     operator_form: str = "DENSE"                  # DENSE (reference: Q2 panels) | IMPLICIT (Jp^T Jp - Q1d^T Q1d from records)
+    stage2_form: str = "PANEL"                    # PANEL (reference: b and SCHUR_JACOBI blocks from the Q2 panels) | IDENTITY
 
     def use_projection_validity_check(self) -> bool:  # solver_options.cpp:41-51
         return self.optimized_cost != "ERROR"
@@ -161,6 +162,7 @@ class LinearizorQR:
         o.device, o.rank, o.nranks = options.device, options.rank, options.nranks
         o.pcg_check_period = options.pcg_check_period
         o.operator_form = {"DENSE": 0, "IMPLICIT": 1}[options.operator_form]
+        o.stage2_form = {"PANEL": 0, "IDENTITY": 1}[options.stage2_form]
         self._opts = o
         pv = ProblemView(bal_problem.num_cameras(), bal_problem.num_landmarks(), bal_problem.num_observations(),
                          bal_problem.lm_off.ctypes.data, bal_problem.obs_cam.ctypes.data, bal_problem.obs_xy.ctypes.data)

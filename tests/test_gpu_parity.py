@@ -2,8 +2,14 @@
 
 Tolerances (relative norm ||a-b||/(||a||+||b||), reference testing/eigen_utils.hpp:104-108):
   single stage, identical inputs:   f32 1e-5 (the reference's default_test_precision, testing/float_utils.hpp:62-69), f64 1e-11
-  after a PCG solve (inc, l_diff):  f32 2e-3, f64 1e-8   (error growth through PCG; CG iteration count +-2)
+  SCHUR_JACOBI inverse blocks:      f32 1e-4 (explicit inverse of a 9x9 block: round-off x its condition number), f64 1e-8
+  after a PCG solve (inc, l_diff):  f32 1e-4, f64 1e-8   (error growth through PCG; CG iteration count +-2)
   indices / counts:                 bit-exact
+Measured on B200 (profiles/r2_f32_trajectory_diag.txt): GPU-f32 vs oracle-f32 inc 3e-6 .. 1e-5, while BOTH are 2e-5 .. 4e-5 from the
+float64 oracle (b 4e-5, H x 2e-4, inverse blocks 1e-4 .. 3e-4): the float32 linearisation itself is the noise floor.
+
+Order: the cheap single-solve checks of every option branch come first, the LM-trajectory tests last, so that one
+trajectory failure cannot hide the rest under `pytest -x`.
 """
 import numpy as np
 import pytest
@@ -13,7 +19,8 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 TOL1 = {np.float32: 1e-5, np.float64: 1e-11}
-TOLS = {np.float32: 2e-3, np.float64: 1e-8}
+TOLS = {np.float32: 1e-4, np.float64: 1e-8}
+TOLB = {np.float32: 1e-4, np.float64: 1e-8}  # explicit inverse of the preconditioner blocks
 
 
 def make_pair(arrays, dtype, **opt_kw):
@@ -38,6 +45,8 @@ def make_pair(arrays, dtype, **opt_kw):
         okw["use_householder"] = int(so.use_householder_marginalization)
     if "operator_form" in opt_kw:
         so.operator_form = opt_kw["operator_form"]  # device-side choice only: the oracle always does the dense product
+    if "stage2_form" in opt_kw:
+        so.stage2_form = opt_kw["stage2_form"]      # device-side choice only: the oracle always reads the Q2 panel
     if "max_num_iterations" in opt_kw:
         so.max_num_iterations = okw["max_num_iterations"] = opt_kw["max_num_iterations"]
     bp = rb.BalProblem.from_arrays(arrays, dtype)
@@ -90,7 +99,7 @@ def test_stage_parity(small_problem, mixed_problem, dtype, which, qr):
     assert rel_err(lin.get_rhs(), dbg["b"]) < tol * 4
     inv_g, blk_g = lin.get_preconditioner()
     worst = max(rel_err(inv_g[c], dbg["inv_blocks"][c]) for c in range(lin.nc))
-    assert worst < (5e-3 if dtype == np.float32 else 1e-8), worst
+    assert worst < TOLB[dtype], worst
     # blocks in the reference storage layout: Q1 rows, R, Q1^T r, Q2 panel incl. damping rows
     n_all = arrays.track_lengths()
     picks = sorted(set([int(np.argmax(n_all)), int(np.argmin(n_all)), 0, arrays.nl - 1] +
@@ -157,48 +166,42 @@ def test_backup_restore(small_problem):
 
 
 @pytest.mark.parametrize("dtype,kw", [
-    (np.float64, {}),
-    (np.float32, {}),
+    (np.float32, {"preconditioner_type": "JACOBI"}),                    # linearizor_qr.cpp:94-112, 196-237; ipp:554-569
     (np.float64, {"preconditioner_type": "JACOBI"}),
-    (np.float32, {"robust_norm": "HUBER", "huber_parameter": 2.0}),
+    (np.float32, {"robust_norm": "HUBER", "huber_parameter": 2.0}),     # bal_bundle_adjustment_helper.cpp:43-66
+    (np.float64, {"robust_norm": "HUBER", "huber_parameter": 0.5}),
+    (np.float32, {"optimized_cost": "ERROR_VALID"}),                    # use_valid_projections_only, ipp:113
     (np.float64, {"optimized_cost": "ERROR_VALID"}),
-    (np.float64, {"use_householder_marginalization": False}),
-    (np.float64, {"operator_form": "IMPLICIT"}),
+    (np.float32, {"stage2_form": "IDENTITY"}),                          # gradient / blocks through the orthogonality identities
+    (np.float64, {"stage2_form": "IDENTITY"}),
 ])
-def test_lm_trajectory(small_problem, dtype, kw):
-    import rootba_b200 as rb
-    bp, lin, o, so = make_pair(small_problem, dtype, max_num_iterations=6, **kw)
-    summ = rb.bundle_adjust_manual(bp, so, linearizor=lin)
-    rows, term = o.optimize()
-    g_it = summ["iterations"]
-    if dtype == np.float64:
-        assert len(g_it) == len(rows)
-    else:  # f32: the function-tolerance stop (|dcost| <= 1e-6 cost) is decided by round-off at convergence
-        assert abs(len(g_it) - len(rows)) <= 1
-    # f32: the initial synthetic cost is dominated by a few near-camera outliers and carries ~1e-4 of round-off
-    # (oracle-f32 vs oracle-f64, see test_compute_error); f64 pins the trajectory at 1e-9.
-    # f32 trajectories drift apart by a few 1e-3 after several LM iterations (different but equally valid f32
-    # round-off in PCG); the f64 trajectory is the strict check.
-    tol = 5e-3 if dtype == np.float32 else 1e-9
-    cost0 = rows[0]["cost"]
-    prev = cost0
-    for a, b in zip(g_it, rows):
-        assert a["iteration"] == int(b["iteration"])
-        ca = a["cost"]["all"]["error"]
-        # the first steps remove >99% of the initial cost: allow round-off relative to that decrease as well
-        assert abs(ca - b["cost"]) <= tol * b["cost"] + (1e-5 if dtype == np.float32 else 1e-12) * cost0, (a["iteration"], ca, b["cost"])
-        # accept/reject decisions and CG iteration counts are compared while LM still makes real progress; once the
-        # relative cost change drops towards the f32 noise level (< 1e-2) they are decided by round-off in float32.
-        significant = dtype == np.float64 or abs(prev - b["cost"]) > 1e-2 * prev
-        if significant:
-            assert bool(a["step_is_successful"]) == bool(b["step_is_successful"]), a["iteration"]
-            if a["iteration"] > 0:
-                # the zeta stopping rule is a threshold on rounded quantities: +-2 in f64, +-30% in f32
-                slack = 2 if dtype == np.float64 else max(2, int(0.3 * b["cg_iterations"]))
-                assert abs(a["linear_solver_iterations"] - int(b["cg_iterations"])) <= slack, a["iteration"]
-        prev = b["cost"]
-    assert g_it[-1]["cost"]["all"]["error"] < 0.2 * g_it[0]["cost"]["all"]["error"]
-    assert abs(g_it[-1]["cost"]["all"]["error"] - rows[-1]["cost"]) <= max(tol, 1e-6) * rows[-1]["cost"]
+def test_option_branches_single_solve(small_problem, dtype, kw):
+    """one linearize + solve + apply per option branch the reference ships, against the oracle with the same option"""
+    bp, lin, o, _ = make_pair(small_problem, dtype, **kw)
+    tol = TOL1[dtype]
+    eg, ec = lin.compute_error(), o.compute_error()
+    assert eg["valid"]["num_obs"] == ec["valid"]["num_obs"] and eg["all"]["num_obs"] == ec["all"]["num_obs"]
+    assert abs(eg["all"]["error"] - ec["all"]["error"]) <= (20 * tol) * ec["all"]["error"]
+    lin.linearize(); assert o.linearize()
+    assert rel_err(lin.get_jacobian_scaling()[0], o.get_scaling()) < tol
+    lam = 1e-2
+    inc_g = lin.solve(lam)
+    inc_c, dbg = o.solve(lam, want_debug=True)
+    assert rel_err(lin.get_rhs(), dbg["b"]) < tol * 4
+    inv_g, _ = lin.get_preconditioner()
+    # the identity form cancels (Jp^T Jp - Q1d^T Q1d): one decade more in float32, see DESIGN.md section 2
+    tb = TOLB[dtype] * (10 if kw.get("stage2_form") == "IDENTITY" and dtype == np.float32 else 1)
+    assert max(rel_err(inv_g[c], dbg["inv_blocks"][c]) for c in range(lin.nc)) < tb
+    x = np.random.default_rng(5).uniform(-1, 1, 9 * lin.nc).astype(dtype)
+    assert rel_err(lin.right_multiply(x), o.right_multiply(x)) < tol * 4
+    assert abs(lin.last_cg.num_iterations - dbg["cg_iterations"]) <= 2
+    assert lin.last_cg.termination_type == dbg["cg_termination"]
+    assert rel_err(inc_g, inc_c) < TOLS[dtype]
+    l_g, l_c = lin.apply(inc_g), o.apply(inc_c)
+    assert abs(l_g - l_c) <= 20 * TOLS[dtype] * abs(l_c)
+    lin.download_state()
+    cams_c, lms_c = o.get_state()
+    assert rel_err(bp.lms, lms_c) < 10 * TOLS[dtype] and rel_err(bp.cams, cams_c) < TOLS[dtype]
     lin.close()
 
 
@@ -305,4 +308,89 @@ def test_full_size_properties():
     summ = rb.bundle_adjust_manual(bp, so, linearizor=lin)
     costs = [it["cost"]["all"]["error"] for it in summ["iterations"] if it.get("step_is_successful")]
     assert costs[-1] < 0.5 * costs[0]
+    lin.close()
+
+
+@pytest.mark.parametrize("config,dtype,kw", [
+    ("ladybug-1723", np.float32, {}),                                      # BASELINE configs[1]
+    ("trafalgar-257", np.float64, {"preconditioner_type": "JACOBI"}),      # BASELINE configs[2]
+])
+def test_full_size_against_oracle(config, dtype, kw):
+    """GPU vs oracle on the BASELINE-size stand-ins: one linearize + solve + back-substitution (the oracle needs seconds)"""
+    from rootba_b200.synthetic import synth_config
+    arrays = synth_config(config)
+    bp, lin, o, _ = make_pair(arrays, dtype, **kw)
+    tol = TOL1[dtype]
+    eg, ec = lin.compute_error(), o.compute_error()
+    assert eg["all"]["num_obs"] == ec["all"]["num_obs"] == arrays.nobs
+    assert abs(eg["all"]["error"] - ec["all"]["error"]) <= 20 * tol * ec["all"]["error"]
+    lin.linearize(); assert o.linearize()
+    assert rel_err(lin.get_jacobian_scaling()[0], o.get_scaling()) < tol
+    lam = 1e-4
+    inc_g = lin.solve(lam)
+    inc_c, dbg = o.solve(lam, want_debug=True)
+    assert rel_err(lin.get_rhs(), dbg["b"]) < tol * 4
+    inv_g, _ = lin.get_preconditioner()
+    assert max(rel_err(inv_g[c], dbg["inv_blocks"][c]) for c in range(lin.nc)) < TOLB[dtype]
+    x = np.random.default_rng(9).uniform(-1, 1, 9 * lin.nc).astype(dtype)
+    assert rel_err(lin.right_multiply(x), o.right_multiply(x)) < tol * 4
+    assert abs(lin.last_cg.num_iterations - dbg["cg_iterations"]) <= 2
+    assert rel_err(inc_g, inc_c) < TOLS[dtype]
+    pose_inc = (np.random.default_rng(2).uniform(-1, 1, 9 * lin.nc) * 0.01).astype(dtype)
+    l_g = lin.back_substitute(pose_inc)
+    l_c, ok = o.back_substitute(pose_inc)
+    assert ok and abs(l_g - l_c) <= tol * 20 * abs(l_c)
+    lin.download_state()
+    assert rel_err(bp.lms, o.get_state()[1]) < tol
+    lin.close()
+
+
+@pytest.mark.parametrize("dtype,kw", [
+    (np.float64, {}),
+    (np.float32, {}),
+    (np.float64, {"preconditioner_type": "JACOBI"}),
+    (np.float32, {"robust_norm": "HUBER", "huber_parameter": 2.0}),
+    (np.float64, {"optimized_cost": "ERROR_VALID"}),
+    (np.float64, {"use_householder_marginalization": False}),
+    (np.float64, {"operator_form": "IMPLICIT"}),
+])
+def test_lm_trajectory(small_problem, dtype, kw):
+    """The whole LM loop (host loop of the Python mirror driving the CUDA path) against the oracle's loop.
+
+    float64 pins the trajectory: same number of logged iterations, every accept/reject decision, cost at 1e-9, PCG
+    iterations +-2.  In float32 the function-tolerance stop (|dcost| <= 1e-6 cost, bal_bundle_adjustment.cpp:174-201) sits
+    at the round-off level of the cost itself -- the float32 ORACLE needs 5, 6 or 9 logged iterations on these problems where
+    the float64 oracle needs 6 (profiles/r2_f32_trajectory_diag.txt), and GPU-f32 / oracle-f32 / oracle-f64 costs agree to
+    1e-6 .. 3e-6 on every iteration they share.  So float32 compares what is above that noise: the cost of every shared
+    iteration at 1e-5 (SURVEY 8c allows 1e-4), decisions and PCG counts while the step still lowers the cost by more than
+    1e-5 relative, and the final cost at 1e-5; the number of noise-level iterations at the end is not compared."""
+    import rootba_b200 as rb
+    bp, lin, o, so = make_pair(small_problem, dtype, max_num_iterations=8, **kw)
+    summ = rb.bundle_adjust_manual(bp, so, linearizor=lin)
+    rows, term = o.optimize()
+    g_it = summ["iterations"]
+    f32 = dtype == np.float32
+    if not f32:
+        assert len(g_it) == len(rows)
+    tol = 1e-5 if f32 else 1e-9
+    noise = 1e-5 if f32 else 0.0
+    cost0 = rows[0]["cost"]
+    prev = cost0
+    compared = 0
+    for a, b in zip(g_it, rows):
+        assert a["iteration"] == int(b["iteration"])
+        ca = a["cost"]["all"]["error"]
+        assert abs(ca - b["cost"]) <= tol * b["cost"] + (1e-7 if f32 else 1e-12) * cost0, (a["iteration"], ca, b["cost"])
+        significant = abs(prev - b["cost"]) > noise * prev
+        if significant:
+            compared += 1
+            assert bool(a["step_is_successful"]) == bool(b["step_is_successful"]), a["iteration"]
+            if a["iteration"] > 0:
+                assert abs(a["linear_solver_iterations"] - int(b["cg_iterations"])) <= 2, a["iteration"]
+        prev = b["cost"]
+    assert compared >= 3
+    assert g_it[-1]["cost"]["all"]["error"] < 0.2 * g_it[0]["cost"]["all"]["error"]
+    best_g = min(it["cost"]["all"]["error"] for it in g_it if it.get("step_is_successful"))
+    best_c = min(r["cost"] for r in rows if r["step_is_successful"])
+    assert abs(best_g - best_c) <= max(tol, 1e-9) * best_c
     lin.close()
