@@ -157,7 +157,9 @@ class GpuE2EBackend(GpuBackend):
 
     def reset(self):
         bp = self.lin.bal_problem
-        bp.cams[:] = self._init[0]; bp.lms[:] = self._init[1]  # the next solve() uploads the state anyway
+        bp.cams[:] = self._init[0]; bp.lms[:] = self._init[1]
+        self.lin.upload_state()  # compute_error / linearize of the new solve run before the next solve() uploads
+        self.h2d += (10 * self.lin.nc + 3 * self.lin.nl) * self.item
 
     def solve(self, lam):
         lin = self.lin

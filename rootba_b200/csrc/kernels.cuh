@@ -66,6 +66,7 @@ struct DevPtrs {
   const TileInfo* tiles; int ntiles;
   const int* sorted_lm;
   const int* slot_cam; const int* slot_lm; const S* slot_xy; int nslots;
+  const int* ypos;   // [nyslots] camera-major position of a y slot (operator output), see Layout::ypos
   // linearization storage
   S* panel;      // Q2^T Jp panels, tile layout
   S* jp;         // [nslots][20] scaled, weighted pose Jacobian rows (2x9) + 2 pad   (16-byte aligned records)
@@ -336,7 +337,9 @@ __device__ __forceinline__ void cam_stage_indices(const int* __restrict__ slots,
   }
   __syncwarp();
 }
-template <class S>
+// DIRECT: the terms of the item are the contiguous run src[9 I.begin .. 9 I.end) (camera-major operator output): no index
+// staging, every load instruction of the warp covers 27 consecutive scalars.
+template <class S, bool DIRECT = false>
 __device__ __forceinline__ void cam_sum_staged(const S* __restrict__ src, const ReduceItem& I, int lane, S* __restrict__ out9,
                                                const int* sidx) {
   const int cnt = I.end - I.begin;
@@ -348,7 +351,8 @@ __device__ __forceinline__ void cam_sum_staged(const S* __restrict__ src, const 
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
       const int e = base + 3 * t + s3;
-      v[t] = (on && e < cnt) ? src[9 * (size_t)sidx[e] + c] : S(0);
+      if (DIRECT) v[t] = (on && e < cnt) ? __ldcg(src + 9 * (size_t)(I.begin + e) + c) : S(0);
+      else v[t] = (on && e < cnt) ? src[9 * (size_t)sidx[e] + c] : S(0);
     }
 #pragma unroll
     for (int t = 0; t < 16; ++t) acc += v[t];
@@ -374,8 +378,10 @@ __global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, c
   __shared__ int sidx_all[8][SEG_LEN];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb)
-    cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb) {
+    if (slots) cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+    else cam_sum_staged<S, true>(src, items[it], lane, partial + 9 * (size_t)it, nullptr);  // camera-major source
+  }
 }
 
 // Same, and the warp that completes the LAST segment of a camera (arrival counter) adds the camera's segment sums in
@@ -390,16 +396,21 @@ __global__ void __launch_bounds__(256) k_cam_reduce_final(const S* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
-  // the slot indices are constant: stage the first item's before the grid dependency is awaited
+  // slots == nullptr: camera-major source (the dense operator's output), no indirection.
+  // Otherwise the slot indices are constant: stage the first item's before the grid dependency is awaited
   const int it0 = blockIdx.x * wpb + (threadIdx.x >> 5);
-  if (it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
+  if (slots && it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (done && *done) return;
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int it = it0; it < nitems; it += gridDim.x * wpb) {
     const ReduceItem I = items[it];
-    if (it != it0) cam_stage_indices<S>(slots, I, lane, sidx_all[threadIdx.x >> 5]);
-    cam_sum_staged(src, I, lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+    if (slots) {
+      if (it != it0) cam_stage_indices<S>(slots, I, lane, sidx_all[threadIdx.x >> 5]);
+      cam_sum_staged<S, false>(src, I, lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+    } else {
+      cam_sum_staged<S, true>(src, I, lane, partial + 9 * (size_t)it, nullptr);
+    }
     const int i0 = cam_item_ptr[I.cam], i1 = cam_item_ptr[I.cam + 1];
     if (i1 - i0 == 1) {
       if (lane < 9) y[9 * (size_t)I.cam + lane] = partial[9 * (size_t)it + lane];
@@ -1390,7 +1401,8 @@ __device__ __forceinline__ void matvec_item(const DevPtrs<S>& D, const MatvecIte
     int g2 = 0, c = lane;
     while (c >= ncols) { c -= ncols; ++g2; }
     while (g2 < T.nvalid) {
-      D.yobs[9 * (size_t)(it.yslot_base + g2 * n) + c] = xs[g2 * CS + c];
+      const int i = c / 9;
+      D.yobs[9 * (size_t)__ldg(D.ypos + it.yslot_base + g2 * n + i) + (c - 9 * i)] = xs[g2 * CS + c];
       c += 32;
       while (c >= ncols) { c -= ncols; ++g2; }
     }
@@ -1433,7 +1445,7 @@ __device__ __forceinline__ void matvec_item_generic(const DevPtrs<S>& D, const M
     }
   }
   __syncwarp();
-  for (int c = lane; c < ncols; c += 32) D.yobs[9 * (size_t)it.yslot_base + c] = ys[c];
+  for (int c = lane; c < ncols; c += 32) D.yobs[9 * (size_t)__ldg(D.ypos + it.yslot_base + c / 9) + c % 9] = ys[c];
   __syncwarp();
 }
 
@@ -1610,13 +1622,23 @@ __device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const Matve
     stream_produce<S, NS, STAGE_BYTES>(ps, D, items, item_end, item_stride, ring, bars, lane);
   }
   // ---- y: each lane writes the columns it owns (contiguous inside a group) ----
+  // (camera-major destination D.ypos: the terms of one camera end up contiguous for the reduction kernel; the index loads
+  // happen here, after the rows, so that they do not occupy registers during the stream -- the ring already holds the
+  // next item's first stages, the HBM stream does not wait for them)
   if (active) {
-    S* yo = D.yobs + 9 * (size_t)(it.yslot_base + g * n);
+    const int* __restrict__ yp = D.ypos + it.yslot_base + g * n;
+    const int step = 2 * G;
+    const int di = step / 9, dp = step - 9 * di;
+    int c = 2 * j;
+    int i = c / 9, p = c - 9 * i;
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      const int c = 2 * j + 2 * G * k;
-      if (c < ncols) yo[c] = yv[k].x;
-      if (c + 1 < ncols) yo[c + 1] = yv[k].y;
+    for (int k = 0; k < KP; ++k) {  // 9 * nyslots < 2^32 is checked at create
+      const bool v0 = c < ncols, v1 = (c + 1) < ncols;
+      const int i1 = (p == 8) ? i + 1 : i, p1 = (p == 8) ? 0 : p + 1;
+      if (v0) D.yobs[9u * (uint32_t)__ldg(yp + i) + p] = yv[k].x;
+      if (v1) D.yobs[9u * (uint32_t)__ldg(yp + i1) + p1] = yv[k].y;
+      c += step; i += di; p += dp;
+      if (p >= 9) { p -= 9; ++i; }
     }
   }
 }
@@ -1957,9 +1979,47 @@ __global__ void k_cam_final9(const S* __restrict__ partial, const int* __restric
 // camera is exchanged through shared memory.  Larger problems loop over rounds and re-read from global memory.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cluster_sync_all() {
-  __threadfence();
   asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// store a double into the same shared-memory variable of CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ void st_dsmem_f64(const double* local, uint32_t rank, double v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"((uint32_t)__cvta_generic_to_shared(local)), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+}
+constexpr int CL_MAX = 16;  // largest cluster of the PCG vector kernel
+// Cluster-wide sums without global memory: every CTA block-reduces NV doubles per thread and stores its totals into slot
+// [k0 + v][own rank] of EVERY CTA's `cl` array through distributed shared memory; after the next cluster barrier
+// cluster_total() adds the per-CTA totals in rank order (bit-identical in every CTA).
+template <int NV>
+__device__ __forceinline__ void cluster_publish(double (&v)[NV], double (*cl)[CL_MAX], int k0) {
+  __shared__ double red[32][NV];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[w][k] = v[k];
+  __syncthreads();
+  const uint32_t me = cluster_ctarank(), nr = cluster_nctarank();
+  if (threadIdx.x < nr) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0;
+      for (int q = 0; q < nw; ++q) s += red[q][k];
+      st_dsmem_f64(&cl[k0 + k][me], threadIdx.x, s);
+    }
+  }
+  __syncthreads();  // red may be reused by the next publish
+}
+__device__ __forceinline__ double cluster_total(double (*cl)[CL_MAX], int k) {
+  const uint32_t nr = cluster_nctarank();
+  double s = 0;
+  for (uint32_t r = 0; r < nr; ++r) s += cl[k][r];
+  return s;
 }
 
 constexpr int VEC_THREADS = 512;
@@ -1993,6 +2053,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
                                                          double eta, int min_it, int is_last, int pdl, PeerComm pc, int seq) {
   __shared__ S sr[VEC_THREADS * VEC_EPT + 16];
   __shared__ int peer_fail;
+  __shared__ double cl[4][CL_MAX];  // per-CTA totals of p.q | r.z | x.(b + r) | r.r, exchanged through distributed shared memory
   const int tid = threadIdx.x;
   const int cams_per_block = (D.nc + gridDim.x - 1) / gridDim.x;
   const int cam0 = min(D.nc, (int)blockIdx.x * cams_per_block);
@@ -2019,6 +2080,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (st->done) return;
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  cluster_sync_all();  // every CTA of the cluster runs (and stays) before the first distributed-shared-memory store
   double alpha = 0;
   const bool peers = pc.nranks > 1 && mode != 3;
   const int slot_off = (seq & 1) * 9 * D.nc;
@@ -2070,12 +2132,12 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
         acc += (double)(vv * q);
       }
     }
-    if (mode != 2) block_sum_store4(acc, part, 0);
+    { double a1[1] = {acc}; cluster_publish<1>(a1, cl, 0); }
     cluster_sync_all();
   }
   // ---- P2 ----
   if (mode == 0 || mode == 1) {
-    const double pq = block_sum_partials(part, gridDim.x, 4, 0);
+    const double pq = cluster_total(cl, 0);
     bool fail = false;
     int term = 0, reason = 0;
     if (pq <= 0 || isinf(pq)) { fail = true; term = 0; reason = 5; }
@@ -2156,19 +2218,17 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
       bb += (double)(r2 * r2);
     }
   }
-  block_sum_store4(rz, part, 1);
-  block_sum_store4(xbr, part, 2);
-  block_sum_store4(bb, part, 3);
+  { double a3[3] = {rz, xbr, bb}; cluster_publish<3>(a3, cl, 1); }
   cluster_sync_all();
   // ---- P3 ----
-  const double rho_new = block_sum_partials(part, gridDim.x, 4, 1);
+  const double rho_new = cluster_total(cl, 1);
   int done = 0, term = 0, reason = 0;
   double q1 = 0, zeta = 0, beta = 0, norm_b = 0;
   if (mode == 3) {
-    norm_b = sqrt(block_sum_partials(part, gridDim.x, 4, 3));
+    norm_b = sqrt(cluster_total(cl, 3));
     if (norm_b == 0.0) { done = 1; term = 1; reason = 2; }
   } else {
-    const double xbr_t = block_sum_partials(part, gridDim.x, 4, 2);
+    const double xbr_t = cluster_total(cl, 2);
     q1 = -xbr_t;
     zeta = (double)i * (q1 - st->q0[cur]) / q1;
     if (zeta < eta && i >= min_it) { done = 1; term = 1; reason = 1; }

@@ -74,6 +74,8 @@ struct Layout {
   CameraCSR csr_obs;               // over observation slots (gradient, column norms, preconditioner)
   CameraCSR csr_y;                 // over y slots (matvec); equals csr_obs when no track is chunked
   bool csr_y_is_obs = true;
+  std::vector<int> ypos;           // [nyslots] position of a y slot in the camera-major order of csr_y (-1 for padding): the
+                                   // operator writes its per-observation output there, so that a camera's terms are contiguous
   std::vector<ReduceItem> pb_items;   // csr_obs slot list cut into segments of PB_SEG_LEN (preconditioner blocks)
   std::vector<int> pb_cam_item_ptr;   // [nc + 1]
   int k1_scratch_per_warp = 0;     // scalars of shared memory per warp for the linearize+QR kernel
@@ -260,6 +262,9 @@ inline std::string build_layout(int nc, int nl, const int64_t* lm_off, const int
     std::vector<int> ocam(ycam.begin(), ycam.begin() + L.nslots);
     build_csr(nc, L.nslots, ocam, L.csr_obs);
     if (!L.csr_y_is_obs) build_csr(nc, L.nyslots, ycam, L.csr_y);
+    const CameraCSR& cy = L.csr_y_is_obs ? L.csr_obs : L.csr_y;
+    L.ypos.assign(L.nyslots, -1);
+    for (size_t e = 0; e < cy.slots.size(); ++e) L.ypos[cy.slots[e]] = (int)e;
     L.pb_cam_item_ptr.assign(nc + 1, 0);
     for (int c = 0; c < nc; ++c) {
       L.pb_cam_item_ptr[c] = (int)L.pb_items.size();

@@ -224,6 +224,7 @@ struct Solver : rba_handle {
     TRY(upload(&d_slot_cam, L.slot_cam));
     TRY(upload(&d_slot_lm, L.slot_lm));
     TRY(upload(&d_xy, xy));
+    { int* d_ypos; TRY(upload(&d_ypos, L.ypos)); D.ypos = d_ypos; }
     TRY(upload(&d_items, L.items));
     TRY(upload(&d_csr_obs_slots, L.csr_obs.slots));
     TRY(upload(&d_csr_obs_items, L.csr_obs.items));
@@ -252,7 +253,7 @@ struct Solver : rba_handle {
       imp_grid = std::max(1, std::min((imp_tile_split + IMP_WARPS - 1) / IMP_WARPS, sm_count * std::max(1, bps)));
     }
     if (implicit_op) { op_slots = d_csr_obs_slots; op_items = d_csr_obs_items; op_item_ptr = d_csr_obs_item_ptr; n_op_items = n_obs_items; }
-    else { op_slots = d_csr_y_slots; op_items = d_csr_y_items; op_item_ptr = d_csr_y_item_ptr; n_op_items = n_y_items; }
+    else { op_slots = nullptr /* camera-major output, Layout::ypos */; op_items = d_csr_y_items; op_item_ptr = d_csr_y_item_ptr; n_op_items = n_y_items; }
     TRY(upload(&d_pb_items, L.pb_items));
     TRY(upload(&d_pb_item_ptr, L.pb_cam_item_ptr));
     n_pb_items = (int)L.pb_items.size();
@@ -276,6 +277,7 @@ struct Solver : rba_handle {
     }
     for (S** v : {&D.diag2, &D.scaling, &D.b, &D.x, &D.r, &D.z, &D.p, &D.q, &D.y, &D.inc}) TRY(dalloc(v, (size_t)9 * nc));
     TRY(dalloc(&D.blocks, (size_t)81 * nc)); TRY(dalloc(&D.jblocks, (size_t)81 * nc)); TRY(dalloc(&D.inv, (size_t)81 * nc));
+    if ((long long)9 * L.nyslots >= (1LL << 32)) { g_err = "too many observation slots for 32-bit scatter offsets"; return RBA_ERR_UNSUPPORTED; }
     TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
     TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
     TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
@@ -1045,6 +1047,17 @@ int32_t rba_layout_selftest(const rba_problem_view* pv, int32_t rank, int32_t nr
   for (int c = 0; c < pv->num_cameras; ++c)
     for (int e = L.csr_obs.cam_ptr[c]; e < L.csr_obs.cam_ptr[c + 1]; ++e)
       if (L.slot_cam[L.csr_obs.slots[e]] != c || L.slot_lm[L.csr_obs.slots[e]] < 0) return fail("observation CSR camera");
+  {
+    const CameraCSR& cy = L.csr_y_is_obs ? L.csr_obs : L.csr_y;
+    if ((int)L.ypos.size() != L.nyslots) return fail("ypos size");
+    std::vector<char> hit(cy.slots.size(), 0);
+    for (int s2 = 0; s2 < L.nyslots; ++s2) {
+      const int e = L.ypos[s2];
+      if (e < 0) continue;
+      if (e >= (int)cy.slots.size() || cy.slots[e] != s2 || hit[e]++) return fail("ypos is not the inverse of the camera-major slot order");
+    }
+    for (char c : hit) if (!c) return fail("camera-major position without a y slot");
+  }
   if (!L.csr_y_is_obs) {
     long long expect = 0;
     for (const MatvecItem& it : L.items) expect += (long long)L.tiles[it.tile].nvalid * L.tiles[it.tile].n;
