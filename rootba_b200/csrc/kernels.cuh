@@ -66,7 +66,6 @@ struct DevPtrs {
   const TileInfo* tiles; int ntiles;
   const int* sorted_lm;
   const int* slot_cam; const int* slot_lm; const S* slot_xy; int nslots;
-  const int* ypos;   // [nyslots] camera-major position of a y slot (operator output), see Layout::ypos
   // linearization storage
   S* panel;      // Q2^T Jp panels, tile layout
   S* jp;         // [nslots][20] scaled, weighted pose Jacobian rows (2x9) + 2 pad   (16-byte aligned records)
@@ -319,6 +318,103 @@ __global__ void __launch_bounds__(256) k_jp_norms(DevPtrs<S> D, KOpts o, int* ba
   }
 }
 
+constexpr int MAX_PEERS = 8;
+
+// Peer-memory exchange (multi-GPU, one box): every rank owns ONE cudaMalloc region that the other ranks map through
+// CUDA IPC.  All exchanges are PUSH based: a rank stores its contribution straight into slot [parity][own rank] of every
+// peer's staging area (posted NVLink writes, they overlap the producing kernel), the next kernel in the stream publishes
+// a sequence number into every peer's flag with st.release.sys, waits for the peers' numbers in its OWN memory
+// (ld.acquire.sys on local memory) and sums the staged contributions in rank order -- bit-identical on every rank, no
+// remote load on the critical path.  Double buffering by the parity of the sequence number makes buffer reuse safe: a
+// rank can only push number s + 2 after it has seen every peer's flag s + 1, which a peer publishes after it has
+// finished reading number s.
+// region layout (bytes):   [0, 64) int yflag[2][8] | [64, 128) int cflag[2][8] | [128, 192) int sflag[2][8]
+//                          [256, 2304) 8-byte sstage[2][8][16] | off_y: S ystage[2][nranks][9 nc] | off_c: S cstage[2][nranks][cmax]
+struct PeerComm {
+  int nranks, rank;
+  char* base[MAX_PEERS];   // base of rank r's region (own entry: local pointer)
+  long long off_y, off_c;  // byte offsets of the staging areas
+  long long cmax;          // elements per (parity, rank) slot of cstage
+};
+constexpr int PEER_SMALL_MAX = 16;
+__device__ __forceinline__ int* peer_flag(const PeerComm& pc, int dest, int family, int par, int src) {
+  return reinterpret_cast<int*>(pc.base[dest] + 64 * family) + par * MAX_PEERS + src;
+}
+template <class S>
+__device__ __forceinline__ S* peer_ystage(const PeerComm& pc, int dest, int par, int src, int nc) {
+  return reinterpret_cast<S*>(pc.base[dest] + pc.off_y) + ((size_t)par * pc.nranks + src) * 9 * (size_t)nc;
+}
+template <class T>
+__device__ __forceinline__ T* peer_cstage(const PeerComm& pc, int dest, int par, int src) {
+  return reinterpret_cast<T*>(pc.base[dest] + pc.off_c) + ((size_t)par * pc.nranks + src) * (size_t)pc.cmax;
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until the local flag of (family, parity, src) has reached seq; false after ~seconds (a peer died)
+__device__ __forceinline__ bool peer_wait(const PeerComm& pc, int family, int par, int src, int seq) {
+  const int* f = peer_flag(pc, pc.rank, family, par, src);
+  long long spins = 0;
+  while (ld_acquire_sys(f) - seq < 0)
+    if (++spins > (1LL << 26)) return false;
+  return true;
+}
+
+// Generic vector all-reduce over peer memory, two kernels so that the kernel boundary is the grid-wide "all my stores are
+// issued" point: k_peer_push stores this rank's vector into every peer's cstage[parity][rank], k_peer_sum publishes the
+// sequence number, waits for the peers' and writes the rank-ordered sum.  Grids are <= the SM count (co-resident: a
+// spinning block can never starve an unscheduled one).
+template <class T>
+__global__ void __launch_bounds__(256) k_peer_push(PeerComm pc, const T* __restrict__ src, long long count, int par) {
+  for (int d = 0; d < pc.nranks; ++d) {
+    T* dst = peer_cstage<T>(pc, d, par, pc.rank);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+}
+template <class T>
+__global__ void __launch_bounds__(256) k_peer_sum(PeerComm pc, T* __restrict__ dst, long long count, int par, int seq, int* fail_flag) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  if (blockIdx.x == 0 && threadIdx.x < pc.nranks) { __threadfence_system(); st_release_sys(peer_flag(pc, threadIdx.x, 1, par, pc.rank), seq); }
+  __syncthreads();
+  if (threadIdx.x < pc.nranks && !peer_wait(pc, 1, par, threadIdx.x, seq)) ok = 0;
+  __syncthreads();
+  if (!ok) { if (threadIdx.x == 0) atomicOr(fail_flag, 2); return; }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    T sacc = 0;
+    for (int r = 0; r < pc.nranks; ++r) sacc += __ldcg(peer_cstage<T>(pc, pc.rank, par, r) + i);
+    dst[i] = sacc;
+  }
+}
+// <= 16 scalars (nd doubles + nf int flags) in ONE single-block kernel: stage, fence, publish, wait, sum.
+__global__ void __launch_bounds__(64) k_peer_small(PeerComm pc, double* vals, int nd, int* flags, int nf, int par, int seq, int* fail_flag) {
+  __shared__ int ok;
+  const int t = threadIdx.x, n = nd + nf;
+  if (t == 0) ok = 1;
+  if (t < n) {
+    const double v = t < nd ? vals[t] : (double)flags[t - nd];
+    for (int d = 0; d < pc.nranks; ++d)
+      reinterpret_cast<double*>(pc.base[d] + 256)[((size_t)par * MAX_PEERS + pc.rank) * PEER_SMALL_MAX + t] = v;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t < pc.nranks) st_release_sys(peer_flag(pc, t, 2, par, pc.rank), seq);
+  if (t < pc.nranks && !peer_wait(pc, 2, par, t, seq)) ok = 0;
+  __syncthreads();
+  if (!ok) { if (t == 0) atomicOr(fail_flag, 2); return; }
+  if (t < n) {
+    double sacc = 0;
+    for (int r = 0; r < pc.nranks; ++r)
+      sacc += __ldcg(reinterpret_cast<const double*>(pc.base[pc.rank] + 256) + ((size_t)par * MAX_PEERS + r) * PEER_SMALL_MAX + t);
+    if (t < nd) vals[t] = sacc; else flags[t - nd] = (int)sacc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // deterministic scatter, phase 2: per-camera segmented sum of 9-vectors
 //   warp per ReduceItem (segment of a camera's slot list) -> partial[item][9]
@@ -337,9 +433,7 @@ __device__ __forceinline__ void cam_stage_indices(const int* __restrict__ slots,
   }
   __syncwarp();
 }
-// DIRECT: the terms of the item are the contiguous run src[9 I.begin .. 9 I.end) (camera-major operator output): no index
-// staging, every load instruction of the warp covers 27 consecutive scalars.
-template <class S, bool DIRECT = false>
+template <class S>
 __device__ __forceinline__ void cam_sum_staged(const S* __restrict__ src, const ReduceItem& I, int lane, S* __restrict__ out9,
                                                const int* sidx) {
   const int cnt = I.end - I.begin;
@@ -351,8 +445,7 @@ __device__ __forceinline__ void cam_sum_staged(const S* __restrict__ src, const 
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
       const int e = base + 3 * t + s3;
-      if (DIRECT) v[t] = (on && e < cnt) ? __ldcg(src + 9 * (size_t)(I.begin + e) + c) : S(0);
-      else v[t] = (on && e < cnt) ? src[9 * (size_t)sidx[e] + c] : S(0);
+      v[t] = (on && e < cnt) ? src[9 * (size_t)sidx[e] + c] : S(0);
     }
 #pragma unroll
     for (int t = 0; t < 16; ++t) acc += v[t];
@@ -378,42 +471,45 @@ __global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, c
   __shared__ int sidx_all[8][SEG_LEN];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb) {
-    if (slots) cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
-    else cam_sum_staged<S, true>(src, items[it], lane, partial + 9 * (size_t)it, nullptr);  // camera-major source
-  }
+  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb)
+    cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
 }
 
 // Same, and the warp that completes the LAST segment of a camera (arrival counter) adds the camera's segment sums in
 // their fixed order and writes y[cam][9]: the result is complete when the kernel ends, deterministic, and needs no
 // second kernel.  cam_cnt must be zero on entry and is left zero.
-template <class S>
+template <class S, bool PEERS>
 __global__ void __launch_bounds__(256) k_cam_reduce_final(const S* __restrict__ src, const int* __restrict__ slots,
                                                            const ReduceItem* __restrict__ items, int nitems,
                                                            const int* __restrict__ cam_item_ptr, S* __restrict__ partial,
-                                                           int* cam_cnt, S* __restrict__ y, const int* done, int pdl) {
+                                                           int* cam_cnt, S* __restrict__ y, const int* done, int pdl,
+                                                           PeerComm pc, int seq, int nc) {
   __shared__ int sidx_all[8][SEG_LEN];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
-  // slots == nullptr: camera-major source (the dense operator's output), no indirection.
-  // Otherwise the slot indices are constant: stage the first item's before the grid dependency is awaited
+  // the slot indices are constant: stage the first item's before the grid dependency is awaited
   const int it0 = blockIdx.x * wpb + (threadIdx.x >> 5);
-  if (slots && it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
+  if (it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (done && *done) return;
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int it = it0; it < nitems; it += gridDim.x * wpb) {
     const ReduceItem I = items[it];
-    if (slots) {
-      if (it != it0) cam_stage_indices<S>(slots, I, lane, sidx_all[threadIdx.x >> 5]);
-      cam_sum_staged<S, false>(src, I, lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
-    } else {
-      cam_sum_staged<S, true>(src, I, lane, partial + 9 * (size_t)it, nullptr);
-    }
+    if (it != it0) cam_stage_indices<S>(slots, I, lane, sidx_all[threadIdx.x >> 5]);
+    cam_sum_staged(src, I, lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
     const int i0 = cam_item_ptr[I.cam], i1 = cam_item_ptr[I.cam + 1];
+    // the camera's sum goes to y, or (several shards, peer exchange) into slot [parity][own rank] of EVERY rank's staging
+    // area; cameras without observations in this shard are never written and stay zero there
+    auto emit = [&](S v) {
+      if constexpr (PEERS) {
+        for (int d = 0; d < pc.nranks; ++d) peer_ystage<S>(pc, d, seq & 1, pc.rank, nc)[9 * (size_t)I.cam + lane] = v;
+      } else {
+        y[9 * (size_t)I.cam + lane] = v;
+      }
+    };
     if (i1 - i0 == 1) {
-      if (lane < 9) y[9 * (size_t)I.cam + lane] = partial[9 * (size_t)it + lane];
+      if (lane < 9) emit(partial[9 * (size_t)it + lane]);
       continue;
     }
     __threadfence();
@@ -425,7 +521,7 @@ __global__ void __launch_bounds__(256) k_cam_reduce_final(const S* __restrict__ 
       if (lane < 9) {
         S sacc = 0;
         for (int q = i0; q < i1; ++q) sacc += __ldcg(partial + 9 * (size_t)q + lane);
-        y[9 * (size_t)I.cam + lane] = sacc;
+        emit(sacc);
       }
       if (lane == 0) cam_cnt[I.cam] = 0;
     }
@@ -1401,8 +1497,7 @@ __device__ __forceinline__ void matvec_item(const DevPtrs<S>& D, const MatvecIte
     int g2 = 0, c = lane;
     while (c >= ncols) { c -= ncols; ++g2; }
     while (g2 < T.nvalid) {
-      const int i = c / 9;
-      D.yobs[9 * (size_t)__ldg(D.ypos + it.yslot_base + g2 * n + i) + (c - 9 * i)] = xs[g2 * CS + c];
+      D.yobs[9 * (size_t)(it.yslot_base + g2 * n) + c] = xs[g2 * CS + c];
       c += 32;
       while (c >= ncols) { c -= ncols; ++g2; }
     }
@@ -1445,7 +1540,7 @@ __device__ __forceinline__ void matvec_item_generic(const DevPtrs<S>& D, const M
     }
   }
   __syncwarp();
-  for (int c = lane; c < ncols; c += 32) D.yobs[9 * (size_t)__ldg(D.ypos + it.yslot_base + c / 9) + c % 9] = ys[c];
+  for (int c = lane; c < ncols; c += 32) D.yobs[9 * (size_t)it.yslot_base + c] = ys[c];
   __syncwarp();
 }
 
@@ -1622,23 +1717,13 @@ __device__ __forceinline__ void matvec_item_tma(const DevPtrs<S>& D, const Matve
     stream_produce<S, NS, STAGE_BYTES>(ps, D, items, item_end, item_stride, ring, bars, lane);
   }
   // ---- y: each lane writes the columns it owns (contiguous inside a group) ----
-  // (camera-major destination D.ypos: the terms of one camera end up contiguous for the reduction kernel; the index loads
-  // happen here, after the rows, so that they do not occupy registers during the stream -- the ring already holds the
-  // next item's first stages, the HBM stream does not wait for them)
   if (active) {
-    const int* __restrict__ yp = D.ypos + it.yslot_base + g * n;
-    const int step = 2 * G;
-    const int di = step / 9, dp = step - 9 * di;
-    int c = 2 * j;
-    int i = c / 9, p = c - 9 * i;
+    S* yo = D.yobs + 9 * (size_t)(it.yslot_base + g * n);
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {  // 9 * nyslots < 2^32 is checked at create
-      const bool v0 = c < ncols, v1 = (c + 1) < ncols;
-      const int i1 = (p == 8) ? i + 1 : i, p1 = (p == 8) ? 0 : p + 1;
-      if (v0) D.yobs[9u * (uint32_t)__ldg(yp + i) + p] = yv[k].x;
-      if (v1) D.yobs[9u * (uint32_t)__ldg(yp + i1) + p1] = yv[k].y;
-      c += step; i += di; p += dp;
-      if (p >= 9) { p -= 9; ++i; }
+    for (int k = 0; k < KP; ++k) {
+      const int c = 2 * j + 2 * G * k;
+      if (c < ncols) yo[c] = yv[k].x;
+      if (c + 1 < ncols) yo[c + 1] = yv[k].y;
     }
   }
 }
@@ -1695,6 +1780,238 @@ __global__ void __launch_bounds__(WARPS * 32, RBA_K4_MINB) k_matvec_small_tma(De
       case 9: matvec_item_tma<S, 9, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
       default: break;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 (dynamic variant, default): the same product and the same per-warp TMA ring, but
+//   * items are claimed from a global queue in order of decreasing size (longest-processing-time-first): the static
+//     round-robin deal leaves warps with 1.6x the mean work on Ladybug-1723 (4.4 items per warp), the queue ends within 3 %;
+//   * everything an item needs is ONE 32-byte record (ItemRec), fetched with cp.async two items ahead into a per-warp ring;
+//   * the camera indices of the NEXT item are loaded at the start of the current one and its x entries in the middle of
+//     it, so an item starts without a dependent global round trip (was: items[q] -> tiles[] -> slot_cam[] -> x[]).
+// queue[0] = next item, queue[1] = warps that have run out of items (the last one resets both for the next launch).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int DYN_KPMAX = 9;
+
+template <class S, int NS, int STAGE_BYTES>
+struct DynStream {
+  const S* src;        // next global address to fetch
+  int rows_left;       // rows of the producer's item not yet requested
+  int row_scalars, rows_per_stage;
+  int prod_item;       // local sequence number of the item the producer is in
+  unsigned issued;
+  uint64_t policy;
+};
+
+// request the next stage of this warp's panel stream; false when the warp's sequence has ended
+template <class S, int NS, int STAGE_BYTES>
+__device__ __forceinline__ bool dyn_produce(DynStream<S, NS, STAGE_BYTES>& ps, const S* __restrict__ panel, const ItemRec* recq,
+                                            unsigned char* ring, uint64_t* bars, int lane) {
+  if (ps.rows_left == 0) {
+    cp_async_wait_all();   // the record of the next item was requested >= one item ago
+    __syncwarp();
+    const ItemRec& R = recq[(ps.prod_item + 1) & 3];
+    if (R.nrows == 0) return false;
+    ++ps.prod_item;
+    ps.row_scalars = R.KP * 64;
+    ps.src = panel + R.panel_off;
+    ps.rows_left = R.nrows;
+    ps.rows_per_stage = max(1, STAGE_BYTES / (int)(ps.row_scalars * sizeof(S)));
+  }
+  const int rows = min(ps.rows_per_stage, ps.rows_left);
+  const uint32_t bytes = (uint32_t)(rows * ps.row_scalars * sizeof(S));
+  const unsigned slot = ps.issued % NS;
+  if (lane == 0) {
+    mbar_expect_tx(&bars[slot], bytes);
+    bulk_g2s(ring + (size_t)slot * STAGE_BYTES, ps.src, bytes, &bars[slot], ps.policy);
+  }
+  ps.src += (size_t)rows * ps.row_scalars;
+  ps.rows_left -= rows;
+  ++ps.issued;
+  return true;
+}
+
+// x offsets (9 cam + p, -1 = padding) of the columns a lane owns in an item
+template <class S>
+__device__ __forceinline__ void dyn_offsets(const DevPtrs<S>& D, const ItemRec& R, int lane, int (&off0)[DYN_KPMAX], int (&off1)[DYN_KPMAX]) {
+  const int n = R.n, G = R.G, KP = R.KP;
+  const int g = lane / G, j = lane - g * G;
+  const bool active = g < R.nvalid && R.nrows > 0;
+  const int ncols = 9 * n;
+  const int slot0 = R.slot_base + g * n;
+  const int step = 2 * G;
+  const int di = step / 9, dp = step - 9 * di;
+  int c = 2 * j;
+  int i = c / 9, p = c - 9 * i;
+#pragma unroll
+  for (int k = 0; k < DYN_KPMAX; ++k) {
+    const bool v0 = active && k < KP && c < ncols, v1 = active && k < KP && (c + 1) < ncols;
+    const int i1 = (p == 8) ? i + 1 : i, p1 = (p == 8) ? 0 : p + 1;
+    const int cam0 = v0 ? __ldg(D.slot_cam + slot0 + i) : 0;
+    const int cam1 = v1 ? __ldg(D.slot_cam + slot0 + i1) : 0;
+    off0[k] = v0 ? 9 * cam0 + p : -1;
+    off1[k] = v1 ? 9 * cam1 + p1 : -1;
+    c += step; i += di; p += dp;
+    if (p >= 9) { p -= 9; ++i; }
+  }
+}
+
+struct DynCtx {
+  const ItemRec* recs; int nitems; int* queue;
+  ItemRec* recq;          // per-warp ring of 4 records (shared memory)
+  int next_claim;         // lane 0: item claimed two ahead (to be fetched into recq)
+  int seq;                // local sequence number of the current item
+};
+
+// one item: rows from the ring; in the middle of it the x entries of the NEXT item are fetched (offsets in xoff0/1 -> values in
+// xn0/xn1), and the record of the item after that is requested
+template <class S, int KP, int NS, int STAGE_BYTES>
+__device__ __forceinline__ void dyn_item(const DevPtrs<S>& D, const ItemRec& R, int lane, const S* __restrict__ xvec,
+                                         const S (&x0)[DYN_KPMAX], const S (&x1)[DYN_KPMAX], int (&noff0)[DYN_KPMAX], int (&noff1)[DYN_KPMAX],
+                                         S (&xn0)[DYN_KPMAX], S (&xn1)[DYN_KPMAX], DynStream<S, NS, STAGE_BYTES>& ps, unsigned& consumed,
+                                         DynCtx& cx, unsigned char* ring, uint64_t* bars) {
+  using V2 = typename ST<S>::V2;
+  const int n = R.n, G = R.G;
+  const int g = lane / G, j = lane - g * G;
+  const int ncols = 9 * n;
+  const bool active = g < R.nvalid;
+  V2 yv[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) yv[k] = mk2(S(0), S(0));
+  int rows_left = R.nrows;
+  constexpr int RPS = (STAGE_BYTES / (int)(KP * 64 * sizeof(S))) > 0 ? (STAGE_BYTES / (int)(KP * 64 * sizeof(S))) : 1;
+  bool mid_done = false;
+  while (rows_left > 0) {
+    const unsigned slot = consumed % NS;
+    mbar_wait(&bars[slot], (consumed / NS) & 1u);
+    const int rows = min(RPS, rows_left);
+    const V2* st = reinterpret_cast<const V2*>(ring + (size_t)slot * STAGE_BYTES) + lane;
+    for (int r = 0; r < rows; ++r) {
+      V2 va[KP];
+#pragma unroll
+      for (int k = 0; k < KP; ++k) va[k] = st[(r * KP + k) * 32];
+      S da0 = 0, da1 = 0;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) { da0 = fma(va[k].x, x0[k], da0); da1 = fma(va[k].y, x1[k], da1); }
+      S da = group_sum_p(da0 + da1, G);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) { yv[k].x = fma(da, va[k].x, yv[k].x); yv[k].y = fma(da, va[k].y, yv[k].y); }
+    }
+    __syncwarp();  // every lane is done reading the stage before it is handed back to the TMA engine
+    ++consumed;
+    rows_left -= rows;
+    dyn_produce<S, NS, STAGE_BYTES>(ps, D.panel, cx.recq, ring, bars, lane);
+    if (!mid_done) {
+      mid_done = true;
+      // the index loads issued at the start of this item have landed: fetch the next item's x entries ...
+#pragma unroll
+      for (int k = 0; k < DYN_KPMAX; ++k) {
+        xn0[k] = noff0[k] >= 0 ? __ldg(xvec + noff0[k]) : S(0);
+        xn1[k] = noff1[k] >= 0 ? __ldg(xvec + noff1[k]) : S(0);
+      }
+      // ... and request the record of the item claimed at the start of this one (sequence number seq + 2)
+      if (lane == 0) {
+        ItemRec* dst = cx.recq + ((cx.seq + 2) & 3);
+        if (cx.next_claim < cx.nitems) {
+          cp_async16(dst, cx.recs + cx.next_claim);
+          cp_async16(reinterpret_cast<char*>(dst) + 16, reinterpret_cast<const char*>(cx.recs + cx.next_claim) + 16);
+        } else {
+          dst->nrows = 0;  // end of this warp's sequence
+        }
+      }
+    }
+  }
+  // ---- y: each lane writes the columns it owns (contiguous inside a group) ----
+  if (active) {
+    S* yo = D.yobs + 9 * (size_t)(R.yslot_base + g * n);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int c = 2 * j + 2 * G * k;
+      if (c < ncols) yo[c] = yv[k].x;
+      if (c + 1 < ncols) yo[c + 1] = yv[k].y;
+    }
+  }
+}
+
+#ifndef RBA_DYN_MINB
+#define RBA_DYN_MINB (sizeof(S) == 4 ? 4 : 2)
+#endif
+template <class S, int WARPS, int NS, int STAGE_BYTES>
+__global__ void __launch_bounds__(WARPS * 32, RBA_DYN_MINB) k_matvec_dyn(DevPtrs<S> D, const ItemRec* __restrict__ recs, int item_begin, int nitems,
+                                                                          int* queue, const S* __restrict__ xvec, const int* done, int pdl) {
+  extern __shared__ __align__(128) unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t bars_all[WARPS][NS];
+  __shared__ __align__(16) ItemRec recq_all[WARPS][4];
+  if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* ring = smem_dyn + (size_t)wib * NS * STAGE_BYTES;
+  uint64_t* bars = bars_all[wib];
+  DynCtx cx;
+  cx.recs = recs; cx.nitems = nitems; cx.queue = queue; cx.recq = recq_all[wib]; cx.seq = 0; cx.next_claim = nitems;
+  // claim the first two items of this warp and fetch their records
+  int q0 = nitems;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    q0 = item_begin + atomicAdd(queue, 2);
+    for (int t = 0; t < 2; ++t) {
+      if (q0 + t < nitems) cx.recq[t] = recs[q0 + t];
+      else cx.recq[t].nrows = 0;
+    }
+    cx.recq[2].nrows = 0; cx.recq[3].nrows = 0;
+  }
+  __syncwarp();
+  DynStream<S, NS, STAGE_BYTES> ps;
+  ps.src = nullptr; ps.rows_left = 0; ps.row_scalars = 0; ps.rows_per_stage = 1; ps.prod_item = -1; ps.issued = 0; ps.policy = l2_evict_first_policy();
+  unsigned consumed = 0;
+  // the panel stream does not depend on the previous kernel: prime the ring, then wait for the grid dependency
+#pragma unroll 1
+  for (int s = 0; s < NS; ++s)
+    if (!dyn_produce<S, NS, STAGE_BYTES>(ps, D.panel, cx.recq, ring, bars, lane)) break;
+  int noff0[DYN_KPMAX], noff1[DYN_KPMAX];
+  dyn_offsets(D, cx.recq[0], lane, noff0, noff1);  // indices are constant: before the dependency as well
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (done && *done) {
+    for (unsigned s = 0; s < ps.issued; ++s) mbar_wait(&bars[s % NS], (s / NS) & 1u);  // drain the copies in flight
+    return;
+  }
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  S x0[DYN_KPMAX], x1[DYN_KPMAX], xn0[DYN_KPMAX], xn1[DYN_KPMAX];
+#pragma unroll
+  for (int k = 0; k < DYN_KPMAX; ++k) {
+    x0[k] = noff0[k] >= 0 ? __ldg(xvec + noff0[k]) : S(0);
+    x1[k] = noff1[k] >= 0 ? __ldg(xvec + noff1[k]) : S(0);
+  }
+  while (true) {
+    const ItemRec R = cx.recq[cx.seq & 3];
+    if (R.nrows == 0) break;
+    // start of an item: index loads of the next item, claim of the one after it (both consumed in the middle of this item)
+    dyn_offsets(D, cx.recq[(cx.seq + 1) & 3], lane, noff0, noff1);
+    if (lane == 0) cx.next_claim = item_begin + atomicAdd(queue, 1);
+    switch (R.KP) {
+      case 5: dyn_item<S, 5, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
+      case 6: dyn_item<S, 6, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
+      case 7: dyn_item<S, 7, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
+      case 8: dyn_item<S, 8, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
+      default: dyn_item<S, 9, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
+    }
+    cp_async_wait_all();
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < DYN_KPMAX; ++k) { x0[k] = xn0[k]; x1[k] = xn1[k]; }
+    ++cx.seq;
+  }
+  // out of items: the last warp of the grid to get here rewinds the queue for the next launch
+  if (lane == 0) {
+    const int total = gridDim.x * WARPS;
+    if (atomicAdd(queue + 1, 1) == total - 1) { queue[0] = 0; queue[1] = 0; }
   }
 }
 
@@ -2024,26 +2341,7 @@ __device__ __forceinline__ double cluster_total(double (*cl)[CL_MAX], int k) {
 
 constexpr int VEC_THREADS = 512;
 constexpr int VEC_EPT = 2;
-constexpr int MAX_PEERS = 8;
 
-// Peer-memory all-reduce fused into the vector step (multi-GPU): every rank owns a double-buffered y [2][9 nc] and a flag
-// pair in cudaMalloc memory that the other ranks of the box map through CUDA IPC.  A rank publishes its camera-reduced y
-// (written by the previous kernel) by storing the application sequence number into its flag with release.sys semantics,
-// waits for the same number in every peer's flag (acquire.sys over NVLink) and then sums all ranks' y in rank order with
-// L1-bypassing loads, so all ranks obtain bit-identical vectors without a separate collective kernel.
-struct PeerComm {
-  int nranks, rank;
-  const void* y[MAX_PEERS];   // base of rank r's [2][9 nc] buffer (own entry: local pointer)
-  int* flag[MAX_PEERS];       // rank r's [2] sequence flags
-};
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 template <class S>
 __device__ __forceinline__ S ld_volatile(const S* p) { return *reinterpret_cast<const volatile S*>(p); }
 
@@ -2053,6 +2351,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
                                                          double eta, int min_it, int is_last, int pdl, PeerComm pc, int seq) {
   __shared__ S sr[VEC_THREADS * VEC_EPT + 16];
   __shared__ int peer_fail;
+  __shared__ double cl_go;          // multi-GPU: CTA 0's verdict on the peer exchange (distributed shared memory)
   __shared__ double cl[4][CL_MAX];  // per-CTA totals of p.q | r.z | x.(b + r) | r.r, exchanged through distributed shared memory
   const int tid = threadIdx.x;
   const int cams_per_block = (D.nc + gridDim.x - 1) / gridDim.x;
@@ -2083,31 +2382,36 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
   cluster_sync_all();  // every CTA of the cluster runs (and stays) before the first distributed-shared-memory store
   double alpha = 0;
   const bool peers = pc.nranks > 1 && mode != 3;
-  const int slot_off = (seq & 1) * 9 * D.nc;
+  const int par = seq & 1;
   if (peers) {
-    // publish this rank's y (complete: the producing kernel has finished) and wait for every peer's
-    if (tid == 0) peer_fail = 0;
-    if (blockIdx.x == 0 && tid == 0) { __threadfence_system(); st_release_sys(pc.flag[pc.rank] + (seq & 1), seq); }
-    __syncthreads();
-    if (tid < pc.nranks && tid != pc.rank) {
-      const int* f = pc.flag[tid] + (seq & 1);
-      long long spins = 0;
-      while (ld_acquire_sys(f) - seq < 0) {
-        if (++spins > (1LL << 27)) { peer_fail = 1; break; }  // ~seconds: a peer died; fail instead of hanging the GPU
+    // The producing kernel (k_cam_reduce_final) has pushed this rank's partial y into every peer's staging area and has
+    // completed.  CTA 0 publishes the sequence number to every rank and waits for the peers' numbers in LOCAL memory;
+    // its verdict reaches the other CTAs through distributed shared memory, so that the whole cluster takes the same path.
+    if (cluster_ctarank() == 0) {
+      if (tid == 0) peer_fail = 0;
+      __syncthreads();
+      if (tid < pc.nranks) {
+        __threadfence_system();
+        st_release_sys(peer_flag(pc, tid, 0, par, pc.rank), seq);
+        if (!peer_wait(pc, 0, par, tid, seq)) peer_fail = 1;
       }
+      __syncthreads();
+      if (tid < (int)cluster_nctarank()) st_dsmem_f64(&cl_go, tid, peer_fail ? -1.0 : 1.0);
     }
-    __syncthreads();
-    if (peer_fail) {  // every CTA sees a failure of its own pollers; the solve is reported as FAILURE
+    cluster_sync_all();
+    if (cl_go < 0) {  // uniform over the cluster: a peer never published (dead rank); the solve is reported as FAILURE
       if (blockIdx.x == 0 && tid == 0) { st->done = 1; st->term = 2; st->reason = 99; st->iter = i; }
       return;
     }
   }
+  const S* ys = peers ? peer_ystage<S>(pc, pc.rank, par, 0, D.nc) : nullptr;
+  const size_t ystride = (size_t)9 * D.nc;
   auto load_y = [&](int e) -> S {
     if (!peers) return __ldcg(D.y + e);
-    S sacc = 0;
+    S sacc = 0;  // rank order: bit-identical on every rank; __ldcg: the slots are written by remote stores, L1 may be stale
 #pragma unroll
     for (int r = 0; r < MAX_PEERS; ++r)
-      if (r < pc.nranks) sacc += ld_volatile(reinterpret_cast<const S*>(pc.y[r]) + slot_off + e);
+      if (r < pc.nranks) sacc += __ldcg(ys + r * ystride + e);
     return sacc;
   };
   if (mode != 3) {

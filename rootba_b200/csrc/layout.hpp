@@ -39,6 +39,17 @@ struct MatvecItem {
   int pad;
 };
 
+// packed per-item record of the dynamically scheduled matvec: everything a warp needs for one item in one 32-byte load
+struct ItemRec {
+  long long panel_off;   // scalar offset of the item's first row inside the panel array
+  int slot_base;         // first observation slot of the tile
+  int yslot_base;        // first y slot of the item
+  short n, G, KP, nvalid;
+  short nrows, pad0;
+  int pad1;
+};
+static_assert(sizeof(ItemRec) == 32, "ItemRec is one 32-byte record");
+
 // segment of a camera's slot list, reduced by one warp
 struct ReduceItem {
   int cam, begin, end;
@@ -70,12 +81,11 @@ struct Layout {
   long long panel_scalars = 0;
   std::vector<MatvecItem> items;   // sorted by decreasing work; [0, n_items_large) have KP > kp_small_max
   int n_items_large = 0;
+  std::vector<ItemRec> item_recs;  // same order as items
   int nyslots = 0;                 // y slots = nslots + slots of extra row chunks
   CameraCSR csr_obs;               // over observation slots (gradient, column norms, preconditioner)
   CameraCSR csr_y;                 // over y slots (matvec); equals csr_obs when no track is chunked
   bool csr_y_is_obs = true;
-  std::vector<int> ypos;           // [nyslots] position of a y slot in the camera-major order of csr_y (-1 for padding): the
-                                   // operator writes its per-observation output there, so that a camera's terms are contiguous
   std::vector<ReduceItem> pb_items;   // csr_obs slot list cut into segments of PB_SEG_LEN (preconditioner blocks)
   std::vector<int> pb_cam_item_ptr;   // [nc + 1]
   int k1_scratch_per_warp = 0;     // scalars of shared memory per warp for the linearize+QR kernel
@@ -257,14 +267,19 @@ inline std::string build_layout(int nc, int nl, const int64_t* lm_off, const int
   });
   L.n_items_large = 0;
   for (auto& it : L.items) if (L.tiles[it.tile].KP > KP_SMALL_MAX) ++L.n_items_large;
+  for (const MatvecItem& it : L.items) {
+    const TileInfo& T = L.tiles[it.tile];
+    ItemRec R;
+    R.panel_off = T.panel_off + (long long)it.row0 * T.KP * 64;
+    R.slot_base = T.slot_base; R.yslot_base = it.yslot_base;
+    R.n = T.n; R.G = T.G; R.KP = T.KP; R.nvalid = T.nvalid; R.nrows = it.nrows; R.pad0 = 0; R.pad1 = 0;
+    L.item_recs.push_back(R);
+  }
   // CSRs
   {
     std::vector<int> ocam(ycam.begin(), ycam.begin() + L.nslots);
     build_csr(nc, L.nslots, ocam, L.csr_obs);
     if (!L.csr_y_is_obs) build_csr(nc, L.nyslots, ycam, L.csr_y);
-    const CameraCSR& cy = L.csr_y_is_obs ? L.csr_obs : L.csr_y;
-    L.ypos.assign(L.nyslots, -1);
-    for (size_t e = 0; e < cy.slots.size(); ++e) L.ypos[cy.slots[e]] = (int)e;
     L.pb_cam_item_ptr.assign(nc + 1, 0);
     for (int c = 0; c < nc; ++c) {
       L.pb_cam_item_ptr[c] = (int)L.pb_items.size();

@@ -90,6 +90,9 @@ struct Solver : rba_handle {
   // device-only helpers
   S* cams_bk = nullptr; S* lms_bk = nullptr;
   MatvecItem* d_items = nullptr;
+  ItemRec* d_item_recs = nullptr;  // packed records of the dynamically scheduled matvec
+  int* d_queue = nullptr;          // [2] its work queue (next item, finished warps); zero between launches
+  bool use_dyn = true;
   int* d_csr_obs_slots = nullptr; ReduceItem* d_csr_obs_items = nullptr; int* d_csr_obs_item_ptr = nullptr;
   int* d_csr_y_slots = nullptr; ReduceItem* d_csr_y_items = nullptr; int* d_csr_y_item_ptr = nullptr;
   int n_obs_items = 0, n_y_items = 0;
@@ -128,11 +131,11 @@ struct Solver : rba_handle {
   NcclApi* nccl = nullptr;
   ncclComm_t comm = nullptr;
   // peer-memory all-reduce fused into the PCG vector kernel
-  S* ybuf = nullptr;             // [2][9 nc], IPC-exported
-  int* yflags = nullptr;         // [2] sequence flags, IPC-exported
+  char* peer_mem = nullptr;      // this rank's exchange region (flags + staging areas, see PeerComm), IPC-exported
+  size_t peer_bytes = 0;
   PeerComm pc{};
   bool peer_ok = false;
-  int ar_seq = 0;
+  int ar_seq = 0, c_seq = 0, s_seq = 0;  // sequence numbers of the three flag families (operator output / vectors / scalars)
   std::vector<void*> ipc_opened;
   static constexpr int EBLOCKS = 592;
   static constexpr int KPMAX = sizeof(S) == 4 ? 16 : 10;
@@ -224,8 +227,9 @@ struct Solver : rba_handle {
     TRY(upload(&d_slot_cam, L.slot_cam));
     TRY(upload(&d_slot_lm, L.slot_lm));
     TRY(upload(&d_xy, xy));
-    { int* d_ypos; TRY(upload(&d_ypos, L.ypos)); D.ypos = d_ypos; }
     TRY(upload(&d_items, L.items));
+    TRY(upload(&d_item_recs, L.item_recs));
+    TRY(dalloc(&d_queue, 2));
     TRY(upload(&d_csr_obs_slots, L.csr_obs.slots));
     TRY(upload(&d_csr_obs_items, L.csr_obs.items));
     TRY(upload(&d_csr_obs_item_ptr, L.csr_obs.cam_item_ptr));
@@ -253,7 +257,7 @@ struct Solver : rba_handle {
       imp_grid = std::max(1, std::min((imp_tile_split + IMP_WARPS - 1) / IMP_WARPS, sm_count * std::max(1, bps)));
     }
     if (implicit_op) { op_slots = d_csr_obs_slots; op_items = d_csr_obs_items; op_item_ptr = d_csr_obs_item_ptr; n_op_items = n_obs_items; }
-    else { op_slots = nullptr /* camera-major output, Layout::ypos */; op_items = d_csr_y_items; op_item_ptr = d_csr_y_item_ptr; n_op_items = n_y_items; }
+    else { op_slots = d_csr_y_slots; op_items = d_csr_y_items; op_item_ptr = d_csr_y_item_ptr; n_op_items = n_y_items; }
     TRY(upload(&d_pb_items, L.pb_items));
     TRY(upload(&d_pb_item_ptr, L.pb_cam_item_ptr));
     n_pb_items = (int)L.pb_items.size();
@@ -277,13 +281,19 @@ struct Solver : rba_handle {
     }
     for (S** v : {&D.diag2, &D.scaling, &D.b, &D.x, &D.r, &D.z, &D.p, &D.q, &D.y, &D.inc}) TRY(dalloc(v, (size_t)9 * nc));
     TRY(dalloc(&D.blocks, (size_t)81 * nc)); TRY(dalloc(&D.jblocks, (size_t)81 * nc)); TRY(dalloc(&D.inv, (size_t)81 * nc));
-    if ((long long)9 * L.nyslots >= (1LL << 32)) { g_err = "too many observation slots for 32-bit scatter offsets"; return RBA_ERR_UNSUPPORTED; }
     TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
     TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
     TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
     TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4)); TRY(dalloc(&d_cam_cnt, (size_t)nc));
-    TRY(dalloc(&ybuf, (size_t)2 * 9 * nc)); TRY(dalloc(&yflags, 4));
     pc.nranks = 1; pc.rank = opt.rank;
+    if (opt.nranks > 1 && opt.nranks <= MAX_PEERS) {
+      pc.off_y = 4096;
+      pc.off_c = pc.off_y + (((long long)2 * opt.nranks * 9 * nc * (long long)sizeof(S) + 255) & ~255LL);
+      pc.cmax = (long long)81 * nc;
+      peer_bytes = (size_t)(pc.off_c + (long long)2 * opt.nranks * pc.cmax * (long long)sizeof(S));
+      TRY(dalloc(&peer_mem, peer_bytes));
+      pc.base[opt.rank] = peer_mem;
+    }
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_state, 1));
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
@@ -345,12 +355,21 @@ struct Solver : rba_handle {
     {
       const char* e = getenv("RBA_MATVEC");
       use_tma = !(e && std::string(e) == "ldg");
+      use_dyn = use_tma && !(e && std::string(e) == "static");  // "static": the round-robin TMA kernel of round 1
+      {
+        // the dynamic kernel relies on every item spanning >= 2 ring stages (see k_matvec_dyn); true for all standard classes
+        for (size_t q = L.n_items_large; q < L.items.size(); ++q) {
+          const int rps = std::max(1, K4_STAGE / (int)(L.item_recs[q].KP * 64 * sizeof(S)));
+          if (L.item_recs[q].nrows <= rps) use_dyn = false;
+        }
+        CU(cudaFuncSetAttribute((k_matvec_dyn<S, K4_WARPS, K4_NS, K4_STAGE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)K4_WARPS * K4_NS * K4_STAGE)));
+      }
       k4_smem_tma = (size_t)K4_WARPS * K4_NS * K4_STAGE;
       if (k4_smem_tma > 220 * 1024) use_tma = false;
       if (use_tma) {
         CU(cudaFuncSetAttribute((k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_tma));
         k4_tma_blocks_per_sm = std::max(1, (int)((220 * 1024) / (k4_smem_tma + 1024)));
-        if (const char* b = getenv("RBA_MATVEC_BLOCKS_PER_SM")) k4_tma_blocks_per_sm = std::max(1, atoi(b));
+        if (const char* b = getenv("RBA_MATVEC_BLOCKS_PER_SM")) { k4_tma_blocks_per_sm = std::max(1, atoi(b)); dyn_blocks_per_sm = std::min(k4_tma_blocks_per_sm, sizeof(S) == 4 ? 4 : 2); }
       }
     }
 #undef TRY
@@ -376,18 +395,39 @@ struct Solver : rba_handle {
   size_t k4_smem_small = 0, k4_smem_tma = 0;
   bool use_tma = true;
   int k4_tma_blocks_per_sm = 2;
+  int dyn_blocks_per_sm = sizeof(S) == 4 ? 4 : 2;
 
   // ------------------------------------------------------------------------------------------
-  int allreduce(void* buf, size_t count, bool is_double) {
+  // sum over the shards, in place, on the solver stream: peer-memory push exchange when the ranks have mapped each other's
+  // regions (rba_ipc_import), else NCCL
+  int allreduce(S* buf, size_t count) {
     if (opt.nranks == 1) return RBA_OK;
+    if (peer_ok && (long long)count <= pc.cmax) {
+      ++c_seq;
+      const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)sm_count, (count + 255) / 256));
+      k_peer_push<S><<<g, 256, 0, stream>>>(pc, buf, (long long)count, c_seq & 1);
+      k_peer_sum<S><<<g, 256, 0, stream>>>(pc, buf, (long long)count, c_seq & 1, c_seq, d_flags);
+      launches += 2;
+      return RBA_OK;
+    }
     if (!comm) { g_err = "rba_comm_init has not been called on a sharded handle"; return RBA_ERR_STATE; }
-    ncclResult_t r = nccl->AllReduce(buf, buf, count, is_double ? ncclDouble : (sizeof(S) == 4 ? ncclFloat : ncclDouble), ncclSum, comm, stream);
+    ncclResult_t r = nccl->AllReduce(buf, buf, count, sizeof(S) == 4 ? ncclFloat : ncclDouble, ncclSum, comm, stream);
     if (r != ncclSuccess) { g_err = std::string("ncclAllReduce: ") + nccl->GetErrorString(r); return RBA_ERR_NCCL; }
     return RBA_OK;
   }
-  int allreduce_flags() {  // OR of the bad flags (sum of ints)
+  // nd doubles (d_red) and the bad flags (d_flags, summed = OR) in one exchange
+  int allreduce_scalars(int nd) {
     if (opt.nranks == 1) return RBA_OK;
-    ncclResult_t r = nccl->AllReduce(d_flags, d_flags, 4, ncclInt, ncclSum, comm, stream);
+    if (peer_ok) {
+      ++s_seq;
+      k_peer_small<<<1, 64, 0, stream>>>(pc, d_red, nd, d_flags, 4, s_seq & 1, s_seq, d_flags);
+      ++launches;
+      return RBA_OK;
+    }
+    if (!comm) { g_err = "rba_comm_init has not been called on a sharded handle"; return RBA_ERR_STATE; }
+    ncclResult_t r = ncclSuccess;
+    if (nd > 0) r = nccl->AllReduce(d_red, d_red, nd, ncclDouble, ncclSum, comm, stream);
+    if (r == ncclSuccess) r = nccl->AllReduce(d_flags, d_flags, 4, ncclInt, ncclSum, comm, stream);
     if (r != ncclSuccess) { g_err = std::string("ncclAllReduce: ") + nccl->GetErrorString(r); return RBA_ERR_NCCL; }
     return RBA_OK;
   }
@@ -405,36 +445,33 @@ struct Solver : rba_handle {
   }
 
   int ipc_export(void* out128) override {
-    cudaIpcMemHandle_t hy, hf;
-    CU(cudaIpcGetMemHandle(&hy, ybuf));
-    CU(cudaIpcGetMemHandle(&hf, yflags));
+    std::memset(out128, 0, 128);
+    if (!peer_mem) return RBA_OK;  // single rank
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, peer_mem));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    std::memcpy(out128, &hy, 64);
-    std::memcpy((char*)out128 + 64, &hf, 64);
+    std::memcpy(out128, &h, 64);
     return RBA_OK;
   }
   int ipc_import(const void* all) override {
     if (opt.nranks == 1) return RBA_OK;
-    if (opt.nranks > MAX_PEERS) { g_err = "peer all-reduce supports at most 8 ranks"; return RBA_ERR_UNSUPPORTED; }
+    if (opt.nranks > MAX_PEERS) { g_err = "the peer-memory exchange supports at most 8 ranks"; return RBA_ERR_UNSUPPORTED; }
     if (const char* e = getenv("RBA_PEER_AR")) if (atoi(e) == 0) return RBA_OK;
     CU(cudaSetDevice(device));
-    pc.nranks = opt.nranks; pc.rank = opt.rank;
     for (int r = 0; r < opt.nranks; ++r) {
-      if (r == opt.rank) { pc.y[r] = ybuf; pc.flag[r] = yflags; continue; }
-      cudaIpcMemHandle_t hy, hf;
-      std::memcpy(&hy, (const char*)all + (size_t)128 * r, 64);
-      std::memcpy(&hf, (const char*)all + (size_t)128 * r + 64, 64);
-      void *py = nullptr, *pf = nullptr;
-      if (cudaIpcOpenMemHandle(&py, hy, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-          cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      if (r == opt.rank) continue;
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const char*)all + (size_t)128 * r, 64);
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         cudaGetLastError();
-        pc.nranks = 1;  // fall back to NCCL for the operator all-reduce
-        g_err = "cudaIpcOpenMemHandle failed; using NCCL for the PCG all-reduce";
-        return RBA_OK;
+        g_err = "cudaIpcOpenMemHandle failed; using NCCL for the reductions across shards";
+        return RBA_OK;  // peer_ok stays false: NCCL
       }
-      ipc_opened.push_back(py); ipc_opened.push_back(pf);
-      pc.y[r] = py; pc.flag[r] = (int*)pf;
+      ipc_opened.push_back(p);
+      pc.base[r] = (char*)p;
     }
+    pc.nranks = opt.nranks; pc.rank = opt.rank;
     peer_ok = true;
     return RBA_OK;
   }
@@ -491,7 +528,7 @@ struct Solver : rba_handle {
     k_cam_reduce<S><<<grid_for(nitems, 8, 8), 256, 0, stream>>>(D.yobs, slots, items, nitems, D.partial, done);
     k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, item_ptr, nc, dst, done, addend);
     launches += 2;
-    return reduce_ranks ? allreduce(dst, (size_t)9 * nc, false) : RBA_OK;
+    return reduce_ranks ? allreduce(dst, (size_t)9 * nc) : RBA_OK;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -502,8 +539,7 @@ struct Solver : rba_handle {
     k_error<S><<<EBLOCKS, 256, 0, stream>>>(D, ko, d_epart, d_flags);
     k_sum_partials<6><<<1, 256, 0, stream>>>(d_epart, EBLOCKS, d_red);
     launches += 2;
-    rc = allreduce(d_red, 6, true); if (rc) return rc;
-    rc = allreduce_flags(); if (rc) return rc;
+    rc = allreduce_scalars(6); if (rc) return rc;
     CU(cudaMemcpyAsync(h_red, d_red, 6 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     rc = stop(ev_error); if (rc) return rc;
@@ -546,7 +582,7 @@ struct Solver : rba_handle {
       rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b0, nullptr, nullptr, false); if (rc) return rc;
       if (want_blocks) { rc = precond_blocks(3, D.blocks0, nullptr, false); if (rc) return rc; }
     }
-    rc = allreduce_flags(); if (rc) return rc;
+    rc = allreduce_scalars(0); if (rc) return rc;
     CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     rc = stop(ev_stage1); if (rc) return rc;
     CU(cudaStreamSynchronize(stream));
@@ -572,11 +608,12 @@ struct Solver : rba_handle {
     }
     k_precond_final<S><<<(45 * nc + 255) / 256, 256, 0, stream>>>(D.pblk, d_pb_item_ptr, nc, addend, dst);
     launches += 2;
-    return reduce_ranks ? allreduce(dst, (size_t)81 * nc, false) : RBA_OK;
+    return reduce_ranks ? allreduce(dst, (size_t)81 * nc) : RBA_OK;
   }
 
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
   void matvec_launch(const S* xvec, const int* done) {
+    if (use_dyn) cudaMemsetAsync(d_queue, 0, 2 * sizeof(int), stream);  // a PCG solve that stopped early may have left claims behind
     matvec_kernels(xvec, done);
     k_cam_reduce<S><<<grid_for(n_op_items, 8, 8), 256, 0, stream>>>(D.yobs, op_slots, op_items, n_op_items, D.partial, done);
     ++launches;
@@ -599,7 +636,11 @@ struct Solver : rba_handle {
           D, d_items, 0, L.n_items_large, L.k4_scratch_per_warp, xvec, done);
       ++launches;
     }
-    if (nitems > L.n_items_large) {
+    if (nitems > L.n_items_large && use_dyn) {
+      const bool p = pdl && use_pdl && L.n_items_large == 0;
+      launch_ex(k_matvec_dyn<S, K4_WARPS, K4_NS, K4_STAGE>, sm_count * dyn_blocks_per_sm, K4_WARPS * 32, (size_t)K4_WARPS * K4_NS * K4_STAGE, p, 1,
+                D, (const ItemRec*)d_item_recs, L.n_items_large, nitems, d_queue, xvec, done, (int)p);
+    } else if (nitems > L.n_items_large) {
       if (use_tma) {
         launch_ex(k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>, grid_for(nitems - L.n_items_large, K4_WARPS, k4_tma_blocks_per_sm), K4_WARPS * 32,
                   k4_smem_tma, pdl && use_pdl && L.n_items_large == 0, 1, D, (const MatvecItem*)d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done,
@@ -622,16 +663,17 @@ struct Solver : rba_handle {
   int pcg_apply(int i, int mode, int is_last, S lambda) {
     const bool fused = opt.nranks > 1 && peer_ok;
     if (fused) ++ar_seq;
-    S* ydst = fused ? ybuf + (size_t)(ar_seq & 1) * 9 * nc : D.y;
-    // k_cam_reduce_final writes y only for cameras that have observations in this shard; D.y is all-reduced IN PLACE, so
-    // without this the other cameras would carry the previous iteration's global sum into the next all-reduce
+    // NCCL path: k_cam_reduce_final writes y only for cameras that have observations in this shard; D.y is all-reduced IN
+    // PLACE, so without this the other cameras would carry the previous iteration's global sum into the next all-reduce
     if (opt.nranks > 1 && !fused) CU(cudaMemsetAsync(D.y, 0, (size_t)9 * nc * sizeof(S), stream));
-    int rc = launch_ex(k_cam_reduce_final<S>, grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
-                       op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, ydst, (const int*)&d_state->done, (int)use_pdl);
+    int rc = fused ? launch_ex((k_cam_reduce_final<S, true>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
+                               op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, ar_seq, nc)
+                   : launch_ex((k_cam_reduce_final<S, false>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
+                               op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, ar_seq, nc);
     if (rc) return rc;
     if (opt.nranks == 1) return pcg_vec(i, mode, true, is_last, lambda);
     if (fused) return pcg_vec(i, mode, true, is_last, lambda, true);
-    rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
+    rc = allreduce(D.y, (size_t)9 * nc); if (rc) return rc;
     return pcg_vec(i, mode, false, is_last, lambda);
   }
   // q_out = H vec = sum + lambda vec ; optional partial p.q
@@ -641,7 +683,7 @@ struct Solver : rba_handle {
       ++launches;
     } else {
       k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, op_item_ptr, nc, D.y, st ? &st->done : nullptr);
-      int rc = allreduce(D.y, (size_t)9 * nc, false); if (rc) return rc;
+      int rc = allreduce(D.y, (size_t)9 * nc); if (rc) return rc;
       k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, nullptr, nullptr, D.y, vec, out, lambda, part);
       launches += 2;
     }
@@ -673,6 +715,7 @@ struct Solver : rba_handle {
     // PCG (ref: cg/conjugate_gradient.hpp:113-298 ; linearizor_base.cpp:81-103)
     rc = start(ev_pcg); if (rc) return rc;
     CU(cudaMemsetAsync(d_state, 0, sizeof(PcgState), stream));
+    if (use_dyn) CU(cudaMemsetAsync(d_queue, 0, 2 * sizeof(int), stream));
     const int max_it = std::max(opt.max_linear_solver_iterations, 1);
     const int period = opt.residual_reset_period;
     const int chk = opt.pcg_check_period;
@@ -738,8 +781,7 @@ struct Solver : rba_handle {
     k_back_substitute<S><<<grid, TILE_WARPS * 32, 0, stream>>>(D, D.inc, d_epart, d_flags);
     k_sum_partials<1><<<1, 256, 0, stream>>>(d_epart, grid, d_red);
     launches += 2;
-    rc = allreduce(d_red, 1, true); if (rc) return rc;
-    rc = allreduce_flags(); if (rc) return rc;
+    rc = allreduce_scalars(1); if (rc) return rc;
     rc = stop(ev_backsub); if (rc) return rc;
     rc = start(ev_update); if (rc) return rc;
     if (update_cameras) {
@@ -1047,17 +1089,6 @@ int32_t rba_layout_selftest(const rba_problem_view* pv, int32_t rank, int32_t nr
   for (int c = 0; c < pv->num_cameras; ++c)
     for (int e = L.csr_obs.cam_ptr[c]; e < L.csr_obs.cam_ptr[c + 1]; ++e)
       if (L.slot_cam[L.csr_obs.slots[e]] != c || L.slot_lm[L.csr_obs.slots[e]] < 0) return fail("observation CSR camera");
-  {
-    const CameraCSR& cy = L.csr_y_is_obs ? L.csr_obs : L.csr_y;
-    if ((int)L.ypos.size() != L.nyslots) return fail("ypos size");
-    std::vector<char> hit(cy.slots.size(), 0);
-    for (int s2 = 0; s2 < L.nyslots; ++s2) {
-      const int e = L.ypos[s2];
-      if (e < 0) continue;
-      if (e >= (int)cy.slots.size() || cy.slots[e] != s2 || hit[e]++) return fail("ypos is not the inverse of the camera-major slot order");
-    }
-    for (char c : hit) if (!c) return fail("camera-major position without a y slot");
-  }
   if (!L.csr_y_is_obs) {
     long long expect = 0;
     for (const MatvecItem& it : L.items) expect += (long long)L.tiles[it.tile].nvalid * L.tiles[it.tile].n;
