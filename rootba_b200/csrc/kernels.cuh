@@ -1837,9 +1837,11 @@ __device__ __forceinline__ bool dyn_produce(DynStream<S, NS, STAGE_BYTES>& ps, c
   return true;
 }
 
-// x offsets (9 cam + p, -1 = padding) of the columns a lane owns in an item
-template <class S>
-__device__ __forceinline__ void dyn_offsets(const DevPtrs<S>& D, const ItemRec& R, int lane, int (&off0)[DYN_KPMAX], int (&off1)[DYN_KPMAX]) {
+// Camera indices of the observations behind the columns a lane owns in an item (STAGE 0: raw, predicated loads, nothing
+// consumes them here, so the warp does not wait for the round trip) and, STAGE 1, the x entries themselves.
+template <class S, int STAGE>
+__device__ __forceinline__ void dyn_gather(const DevPtrs<S>& D, const ItemRec& R, int lane, const S* __restrict__ xvec,
+                                           int (&cam0)[DYN_KPMAX], int (&cam1)[DYN_KPMAX], S (&x0)[DYN_KPMAX], S (&x1)[DYN_KPMAX]) {
   const int n = R.n, G = R.G, KP = R.KP;
   const int g = lane / G, j = lane - g * G;
   const bool active = g < R.nvalid && R.nrows > 0;
@@ -1853,10 +1855,15 @@ __device__ __forceinline__ void dyn_offsets(const DevPtrs<S>& D, const ItemRec& 
   for (int k = 0; k < DYN_KPMAX; ++k) {
     const bool v0 = active && k < KP && c < ncols, v1 = active && k < KP && (c + 1) < ncols;
     const int i1 = (p == 8) ? i + 1 : i, p1 = (p == 8) ? 0 : p + 1;
-    const int cam0 = v0 ? __ldg(D.slot_cam + slot0 + i) : 0;
-    const int cam1 = v1 ? __ldg(D.slot_cam + slot0 + i1) : 0;
-    off0[k] = v0 ? 9 * cam0 + p : -1;
-    off1[k] = v1 ? 9 * cam1 + p1 : -1;
+    if (STAGE == 0) {
+      cam0[k] = 0; cam1[k] = 0;
+      if (v0) cam0[k] = __ldg(D.slot_cam + slot0 + i);
+      if (v1) cam1[k] = __ldg(D.slot_cam + slot0 + i1);
+    } else {
+      x0[k] = S(0); x1[k] = S(0);
+      if (v0) x0[k] = __ldg(xvec + 9 * cam0[k] + p);
+      if (v1) x1[k] = __ldg(xvec + 9 * cam1[k] + p1);
+    }
     c += step; i += di; p += dp;
     if (p >= 9) { p -= 9; ++i; }
   }
@@ -1910,11 +1917,7 @@ __device__ __forceinline__ void dyn_item(const DevPtrs<S>& D, const ItemRec& R, 
     if (!mid_done) {
       mid_done = true;
       // the index loads issued at the start of this item have landed: fetch the next item's x entries ...
-#pragma unroll
-      for (int k = 0; k < DYN_KPMAX; ++k) {
-        xn0[k] = noff0[k] >= 0 ? __ldg(xvec + noff0[k]) : S(0);
-        xn1[k] = noff1[k] >= 0 ? __ldg(xvec + noff1[k]) : S(0);
-      }
+      dyn_gather<S, 1>(D, cx.recq[(cx.seq + 1) & 3], lane, xvec, noff0, noff1, xn0, xn1);
       // ... and request the record of the item claimed at the start of this one (sequence number seq + 2)
       if (lane == 0) {
         ItemRec* dst = cx.recq + ((cx.seq + 2) & 3);
@@ -1976,24 +1979,20 @@ __global__ void __launch_bounds__(WARPS * 32, RBA_DYN_MINB) k_matvec_dyn(DevPtrs
   for (int s = 0; s < NS; ++s)
     if (!dyn_produce<S, NS, STAGE_BYTES>(ps, D.panel, cx.recq, ring, bars, lane)) break;
   int noff0[DYN_KPMAX], noff1[DYN_KPMAX];
-  dyn_offsets(D, cx.recq[0], lane, noff0, noff1);  // indices are constant: before the dependency as well
+  S x0[DYN_KPMAX], x1[DYN_KPMAX], xn0[DYN_KPMAX], xn1[DYN_KPMAX];
+  dyn_gather<S, 0>(D, cx.recq[0], lane, xvec, noff0, noff1, x0, x1);  // indices are constant: before the dependency as well
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (done && *done) {
     for (unsigned s = 0; s < ps.issued; ++s) mbar_wait(&bars[s % NS], (s / NS) & 1u);  // drain the copies in flight
     return;
   }
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  S x0[DYN_KPMAX], x1[DYN_KPMAX], xn0[DYN_KPMAX], xn1[DYN_KPMAX];
-#pragma unroll
-  for (int k = 0; k < DYN_KPMAX; ++k) {
-    x0[k] = noff0[k] >= 0 ? __ldg(xvec + noff0[k]) : S(0);
-    x1[k] = noff1[k] >= 0 ? __ldg(xvec + noff1[k]) : S(0);
-  }
+  dyn_gather<S, 1>(D, cx.recq[0], lane, xvec, noff0, noff1, x0, x1);
   while (true) {
     const ItemRec R = cx.recq[cx.seq & 3];
     if (R.nrows == 0) break;
     // start of an item: index loads of the next item, claim of the one after it (both consumed in the middle of this item)
-    dyn_offsets(D, cx.recq[(cx.seq + 1) & 3], lane, noff0, noff1);
+    dyn_gather<S, 0>(D, cx.recq[(cx.seq + 1) & 3], lane, xvec, noff0, noff1, xn0, xn1);
     if (lane == 0) cx.next_claim = item_begin + atomicAdd(queue, 1);
     switch (R.KP) {
       case 5: dyn_item<S, 5, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
