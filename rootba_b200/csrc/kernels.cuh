@@ -335,6 +335,7 @@ struct PeerComm {
   char* base[MAX_PEERS];   // base of rank r's region (own entry: local pointer)
   long long off_y, off_c;  // byte offsets of the staging areas
   long long cmax;          // elements per (parity, rank) slot of cstage
+  int* dead;               // device flag of THIS rank: set when an exchange timed out; every later exchange fails at once
 };
 constexpr int PEER_SMALL_MAX = 16;
 __device__ __forceinline__ int* peer_flag(const PeerComm& pc, int dest, int family, int par, int src) {
@@ -356,12 +357,14 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// wait until the local flag of (family, parity, src) has reached seq; false after ~seconds (a peer died)
+// wait until the local flag of (family, parity, src) has reached seq; false after ~2 s (a peer died) or when an earlier
+// exchange of this rank has already failed (sticky: a dead peer costs one timeout, not one per kernel)
 __device__ __forceinline__ bool peer_wait(const PeerComm& pc, int family, int par, int src, int seq) {
   const int* f = peer_flag(pc, pc.rank, family, par, src);
+  if (*reinterpret_cast<volatile int*>(pc.dead)) return false;
   long long spins = 0;
   while (ld_acquire_sys(f) - seq < 0)
-    if (++spins > (1LL << 26)) return false;
+    if (++spins > (1LL << 22)) { *reinterpret_cast<volatile int*>(pc.dead) = 1; return false; }
   return true;
 }
 
@@ -1780,237 +1783,6 @@ __global__ void __launch_bounds__(WARPS * 32, RBA_K4_MINB) k_matvec_small_tma(De
       case 9: matvec_item_tma<S, 9, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
       default: break;
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4 (dynamic variant, default): the same product and the same per-warp TMA ring, but
-//   * items are claimed from a global queue in order of decreasing size (longest-processing-time-first): the static
-//     round-robin deal leaves warps with 1.6x the mean work on Ladybug-1723 (4.4 items per warp), the queue ends within 3 %;
-//   * everything an item needs is ONE 32-byte record (ItemRec), fetched with cp.async two items ahead into a per-warp ring;
-//   * the camera indices of the NEXT item are loaded at the start of the current one and its x entries in the middle of
-//     it, so an item starts without a dependent global round trip (was: items[q] -> tiles[] -> slot_cam[] -> x[]).
-// queue[0] = next item, queue[1] = warps that have run out of items (the last one resets both for the next launch).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-constexpr int DYN_KPMAX = 9;
-
-template <class S, int NS, int STAGE_BYTES>
-struct DynStream {
-  const S* src;        // next global address to fetch
-  int rows_left;       // rows of the producer's item not yet requested
-  int row_scalars, rows_per_stage;
-  int prod_item;       // local sequence number of the item the producer is in
-  unsigned issued;
-  uint64_t policy;
-};
-
-// request the next stage of this warp's panel stream; false when the warp's sequence has ended
-template <class S, int NS, int STAGE_BYTES>
-__device__ __forceinline__ bool dyn_produce(DynStream<S, NS, STAGE_BYTES>& ps, const S* __restrict__ panel, const ItemRec* recq,
-                                            unsigned char* ring, uint64_t* bars, int lane) {
-  if (ps.rows_left == 0) {
-    cp_async_wait_all();   // the record of the next item was requested >= one item ago
-    __syncwarp();
-    const ItemRec& R = recq[(ps.prod_item + 1) & 3];
-    if (R.nrows == 0) return false;
-    ++ps.prod_item;
-    ps.row_scalars = R.KP * 64;
-    ps.src = panel + R.panel_off;
-    ps.rows_left = R.nrows;
-    ps.rows_per_stage = max(1, STAGE_BYTES / (int)(ps.row_scalars * sizeof(S)));
-  }
-  const int rows = min(ps.rows_per_stage, ps.rows_left);
-  const uint32_t bytes = (uint32_t)(rows * ps.row_scalars * sizeof(S));
-  const unsigned slot = ps.issued % NS;
-  if (lane == 0) {
-    mbar_expect_tx(&bars[slot], bytes);
-    bulk_g2s(ring + (size_t)slot * STAGE_BYTES, ps.src, bytes, &bars[slot], ps.policy);
-  }
-  ps.src += (size_t)rows * ps.row_scalars;
-  ps.rows_left -= rows;
-  ++ps.issued;
-  return true;
-}
-
-// Camera indices of the observations behind the columns a lane owns in an item (STAGE 0: raw, predicated loads, nothing
-// consumes them here, so the warp does not wait for the round trip) and, STAGE 1, the x entries themselves.
-template <class S, int STAGE>
-__device__ __forceinline__ void dyn_gather(const DevPtrs<S>& D, const ItemRec& R, int lane, const S* __restrict__ xvec,
-                                           int (&cam0)[DYN_KPMAX], int (&cam1)[DYN_KPMAX], S (&x0)[DYN_KPMAX], S (&x1)[DYN_KPMAX]) {
-  const int n = R.n, G = R.G, KP = R.KP;
-  const int g = lane / G, j = lane - g * G;
-  const bool active = g < R.nvalid && R.nrows > 0;
-  const int ncols = 9 * n;
-  const int slot0 = R.slot_base + g * n;
-  const int step = 2 * G;
-  const int di = step / 9, dp = step - 9 * di;
-  int c = 2 * j;
-  int i = c / 9, p = c - 9 * i;
-#pragma unroll
-  for (int k = 0; k < DYN_KPMAX; ++k) {
-    const bool v0 = active && k < KP && c < ncols, v1 = active && k < KP && (c + 1) < ncols;
-    const int i1 = (p == 8) ? i + 1 : i, p1 = (p == 8) ? 0 : p + 1;
-    if (STAGE == 0) {
-      cam0[k] = 0; cam1[k] = 0;
-      if (v0) cam0[k] = __ldg(D.slot_cam + slot0 + i);
-      if (v1) cam1[k] = __ldg(D.slot_cam + slot0 + i1);
-    } else {
-      x0[k] = S(0); x1[k] = S(0);
-      if (v0) x0[k] = __ldg(xvec + 9 * cam0[k] + p);
-      if (v1) x1[k] = __ldg(xvec + 9 * cam1[k] + p1);
-    }
-    c += step; i += di; p += dp;
-    if (p >= 9) { p -= 9; ++i; }
-  }
-}
-
-struct DynCtx {
-  const ItemRec* recs; int nitems; int* queue;
-  ItemRec* recq;          // per-warp ring of 4 records (shared memory)
-  int next_claim;         // lane 0: item claimed two ahead (to be fetched into recq)
-  int seq;                // local sequence number of the current item
-};
-
-// one item: rows from the ring; in the middle of it the x entries of the NEXT item are fetched (offsets in xoff0/1 -> values in
-// xn0/xn1), and the record of the item after that is requested
-template <class S, int KP, int NS, int STAGE_BYTES>
-__device__ __forceinline__ void dyn_item(const DevPtrs<S>& D, const ItemRec& R, int lane, const S* __restrict__ xvec,
-                                         const S (&x0)[DYN_KPMAX], const S (&x1)[DYN_KPMAX], int (&noff0)[DYN_KPMAX], int (&noff1)[DYN_KPMAX],
-                                         S (&xn0)[DYN_KPMAX], S (&xn1)[DYN_KPMAX], DynStream<S, NS, STAGE_BYTES>& ps, unsigned& consumed,
-                                         DynCtx& cx, unsigned char* ring, uint64_t* bars) {
-  using V2 = typename ST<S>::V2;
-  const int n = R.n, G = R.G;
-  const int g = lane / G, j = lane - g * G;
-  const int ncols = 9 * n;
-  const bool active = g < R.nvalid;
-  V2 yv[KP];
-#pragma unroll
-  for (int k = 0; k < KP; ++k) yv[k] = mk2(S(0), S(0));
-  int rows_left = R.nrows;
-  constexpr int RPS = (STAGE_BYTES / (int)(KP * 64 * sizeof(S))) > 0 ? (STAGE_BYTES / (int)(KP * 64 * sizeof(S))) : 1;
-  bool mid_done = false;
-  while (rows_left > 0) {
-    const unsigned slot = consumed % NS;
-    mbar_wait(&bars[slot], (consumed / NS) & 1u);
-    const int rows = min(RPS, rows_left);
-    const V2* st = reinterpret_cast<const V2*>(ring + (size_t)slot * STAGE_BYTES) + lane;
-    for (int r = 0; r < rows; ++r) {
-      V2 va[KP];
-#pragma unroll
-      for (int k = 0; k < KP; ++k) va[k] = st[(r * KP + k) * 32];
-      S da0 = 0, da1 = 0;
-#pragma unroll
-      for (int k = 0; k < KP; ++k) { da0 = fma(va[k].x, x0[k], da0); da1 = fma(va[k].y, x1[k], da1); }
-      S da = group_sum_p(da0 + da1, G);
-#pragma unroll
-      for (int k = 0; k < KP; ++k) { yv[k].x = fma(da, va[k].x, yv[k].x); yv[k].y = fma(da, va[k].y, yv[k].y); }
-    }
-    __syncwarp();  // every lane is done reading the stage before it is handed back to the TMA engine
-    ++consumed;
-    rows_left -= rows;
-    dyn_produce<S, NS, STAGE_BYTES>(ps, D.panel, cx.recq, ring, bars, lane);
-    if (!mid_done) {
-      mid_done = true;
-      // the index loads issued at the start of this item have landed: fetch the next item's x entries ...
-      dyn_gather<S, 1>(D, cx.recq[(cx.seq + 1) & 3], lane, xvec, noff0, noff1, xn0, xn1);
-      // ... and request the record of the item claimed at the start of this one (sequence number seq + 2)
-      if (lane == 0) {
-        ItemRec* dst = cx.recq + ((cx.seq + 2) & 3);
-        if (cx.next_claim < cx.nitems) {
-          cp_async16(dst, cx.recs + cx.next_claim);
-          cp_async16(reinterpret_cast<char*>(dst) + 16, reinterpret_cast<const char*>(cx.recs + cx.next_claim) + 16);
-        } else {
-          dst->nrows = 0;  // end of this warp's sequence
-        }
-      }
-    }
-  }
-  // ---- y: each lane writes the columns it owns (contiguous inside a group) ----
-  if (active) {
-    S* yo = D.yobs + 9 * (size_t)(R.yslot_base + g * n);
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      const int c = 2 * j + 2 * G * k;
-      if (c < ncols) yo[c] = yv[k].x;
-      if (c + 1 < ncols) yo[c + 1] = yv[k].y;
-    }
-  }
-}
-
-#ifndef RBA_DYN_MINB
-#define RBA_DYN_MINB (sizeof(S) == 4 ? 4 : 2)
-#endif
-template <class S, int WARPS, int NS, int STAGE_BYTES>
-__global__ void __launch_bounds__(WARPS * 32, RBA_DYN_MINB) k_matvec_dyn(DevPtrs<S> D, const ItemRec* __restrict__ recs, int item_begin, int nitems,
-                                                                          int* queue, const S* __restrict__ xvec, const int* done, int pdl) {
-  extern __shared__ __align__(128) unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t bars_all[WARPS][NS];
-  __shared__ __align__(16) ItemRec recq_all[WARPS][4];
-  if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char* ring = smem_dyn + (size_t)wib * NS * STAGE_BYTES;
-  uint64_t* bars = bars_all[wib];
-  DynCtx cx;
-  cx.recs = recs; cx.nitems = nitems; cx.queue = queue; cx.recq = recq_all[wib]; cx.seq = 0; cx.next_claim = nitems;
-  // claim the first two items of this warp and fetch their records
-  int q0 = nitems;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
-    mbar_fence_init();
-    q0 = item_begin + atomicAdd(queue, 2);
-    for (int t = 0; t < 2; ++t) {
-      if (q0 + t < nitems) cx.recq[t] = recs[q0 + t];
-      else cx.recq[t].nrows = 0;
-    }
-    cx.recq[2].nrows = 0; cx.recq[3].nrows = 0;
-  }
-  __syncwarp();
-  DynStream<S, NS, STAGE_BYTES> ps;
-  ps.src = nullptr; ps.rows_left = 0; ps.row_scalars = 0; ps.rows_per_stage = 1; ps.prod_item = -1; ps.issued = 0; ps.policy = l2_evict_first_policy();
-  unsigned consumed = 0;
-  // the panel stream does not depend on the previous kernel: prime the ring, then wait for the grid dependency
-#pragma unroll 1
-  for (int s = 0; s < NS; ++s)
-    if (!dyn_produce<S, NS, STAGE_BYTES>(ps, D.panel, cx.recq, ring, bars, lane)) break;
-  int noff0[DYN_KPMAX], noff1[DYN_KPMAX];
-  S x0[DYN_KPMAX], x1[DYN_KPMAX], xn0[DYN_KPMAX], xn1[DYN_KPMAX];
-  dyn_gather<S, 0>(D, cx.recq[0], lane, xvec, noff0, noff1, x0, x1);  // indices are constant: before the dependency as well
-  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (done && *done) {
-    for (unsigned s = 0; s < ps.issued; ++s) mbar_wait(&bars[s % NS], (s / NS) & 1u);  // drain the copies in flight
-    return;
-  }
-  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  dyn_gather<S, 1>(D, cx.recq[0], lane, xvec, noff0, noff1, x0, x1);
-  while (true) {
-    const ItemRec R = cx.recq[cx.seq & 3];
-    if (R.nrows == 0) break;
-    // start of an item: index loads of the next item, claim of the one after it (both consumed in the middle of this item)
-    dyn_gather<S, 0>(D, cx.recq[(cx.seq + 1) & 3], lane, xvec, noff0, noff1, xn0, xn1);
-    if (lane == 0) cx.next_claim = item_begin + atomicAdd(queue, 1);
-    switch (R.KP) {
-      case 5: dyn_item<S, 5, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
-      case 6: dyn_item<S, 6, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
-      case 7: dyn_item<S, 7, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
-      case 8: dyn_item<S, 8, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
-      default: dyn_item<S, 9, NS, STAGE_BYTES>(D, R, lane, xvec, x0, x1, noff0, noff1, xn0, xn1, ps, consumed, cx, ring, bars); break;
-    }
-    cp_async_wait_all();
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < DYN_KPMAX; ++k) { x0[k] = xn0[k]; x1[k] = xn1[k]; }
-    ++cx.seq;
-  }
-  // out of items: the last warp of the grid to get here rewinds the queue for the next launch
-  if (lane == 0) {
-    const int total = gridDim.x * WARPS;
-    if (atomicAdd(queue + 1, 1) == total - 1) { queue[0] = 0; queue[1] = 0; }
   }
 }
 

@@ -39,17 +39,6 @@ struct MatvecItem {
   int pad;
 };
 
-// packed per-item record of the dynamically scheduled matvec: everything a warp needs for one item in one 32-byte load
-struct ItemRec {
-  long long panel_off;   // scalar offset of the item's first row inside the panel array
-  int slot_base;         // first observation slot of the tile
-  int yslot_base;        // first y slot of the item
-  short n, G, KP, nvalid;
-  short nrows, pad0;
-  int pad1;
-};
-static_assert(sizeof(ItemRec) == 32, "ItemRec is one 32-byte record");
-
 // segment of a camera's slot list, reduced by one warp
 struct ReduceItem {
   int cam, begin, end;
@@ -81,7 +70,6 @@ struct Layout {
   long long panel_scalars = 0;
   std::vector<MatvecItem> items;   // sorted by decreasing work; [0, n_items_large) have KP > kp_small_max
   int n_items_large = 0;
-  std::vector<ItemRec> item_recs;  // same order as items
   int nyslots = 0;                 // y slots = nslots + slots of extra row chunks
   CameraCSR csr_obs;               // over observation slots (gradient, column norms, preconditioner)
   CameraCSR csr_y;                 // over y slots (matvec); equals csr_obs when no track is chunked
@@ -267,14 +255,6 @@ inline std::string build_layout(int nc, int nl, const int64_t* lm_off, const int
   });
   L.n_items_large = 0;
   for (auto& it : L.items) if (L.tiles[it.tile].KP > KP_SMALL_MAX) ++L.n_items_large;
-  for (const MatvecItem& it : L.items) {
-    const TileInfo& T = L.tiles[it.tile];
-    ItemRec R;
-    R.panel_off = T.panel_off + (long long)it.row0 * T.KP * 64;
-    R.slot_base = T.slot_base; R.yslot_base = it.yslot_base;
-    R.n = T.n; R.G = T.G; R.KP = T.KP; R.nvalid = T.nvalid; R.nrows = it.nrows; R.pad0 = 0; R.pad1 = 0;
-    L.item_recs.push_back(R);
-  }
   // CSRs
   {
     std::vector<int> ocam(ycam.begin(), ycam.begin() + L.nslots);

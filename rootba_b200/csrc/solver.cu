@@ -90,9 +90,6 @@ struct Solver : rba_handle {
   // device-only helpers
   S* cams_bk = nullptr; S* lms_bk = nullptr;
   MatvecItem* d_items = nullptr;
-  ItemRec* d_item_recs = nullptr;  // packed records of the dynamically scheduled matvec
-  int* d_queue = nullptr;          // [2] its work queue (next item, finished warps); zero between launches
-  bool use_dyn = true;
   long long state_version = 0;     // bumped whenever cameras / landmarks change (set_state, apply, restore)
   rba_residual_info error_cache{}; long long error_cache_version = -1; bool error_cache_valid = false;
   int* d_csr_obs_slots = nullptr; ReduceItem* d_csr_obs_items = nullptr; int* d_csr_obs_item_ptr = nullptr;
@@ -230,8 +227,7 @@ struct Solver : rba_handle {
     TRY(upload(&d_slot_lm, L.slot_lm));
     TRY(upload(&d_xy, xy));
     TRY(upload(&d_items, L.items));
-    TRY(upload(&d_item_recs, L.item_recs));
-    TRY(dalloc(&d_queue, 2));
+
     TRY(upload(&d_csr_obs_slots, L.csr_obs.slots));
     TRY(upload(&d_csr_obs_items, L.csr_obs.items));
     TRY(upload(&d_csr_obs_item_ptr, L.csr_obs.cam_item_ptr));
@@ -295,6 +291,7 @@ struct Solver : rba_handle {
       peer_bytes = (size_t)(pc.off_c + (long long)2 * opt.nranks * pc.cmax * (long long)sizeof(S));
       TRY(dalloc(&peer_mem, peer_bytes));
       pc.base[opt.rank] = peer_mem;
+      TRY(dalloc(&pc.dead, 1));
     }
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_state, 1));
@@ -357,21 +354,12 @@ struct Solver : rba_handle {
     {
       const char* e = getenv("RBA_MATVEC");
       use_tma = !(e && std::string(e) == "ldg");
-      use_dyn = use_tma && !(e && std::string(e) == "static");  // "static": the round-robin TMA kernel of round 1
-      {
-        // the dynamic kernel relies on every item spanning >= 2 ring stages (see k_matvec_dyn); true for all standard classes
-        for (size_t q = L.n_items_large; q < L.items.size(); ++q) {
-          const int rps = std::max(1, K4_STAGE / (int)(L.item_recs[q].KP * 64 * sizeof(S)));
-          if (L.item_recs[q].nrows <= rps) use_dyn = false;
-        }
-        CU(cudaFuncSetAttribute((k_matvec_dyn<S, K4_WARPS, K4_NS, K4_STAGE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)K4_WARPS * K4_NS * K4_STAGE)));
-      }
       k4_smem_tma = (size_t)K4_WARPS * K4_NS * K4_STAGE;
       if (k4_smem_tma > 220 * 1024) use_tma = false;
       if (use_tma) {
         CU(cudaFuncSetAttribute((k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_tma));
         k4_tma_blocks_per_sm = std::max(1, (int)((220 * 1024) / (k4_smem_tma + 1024)));
-        if (const char* b = getenv("RBA_MATVEC_BLOCKS_PER_SM")) { k4_tma_blocks_per_sm = std::max(1, atoi(b)); dyn_blocks_per_sm = std::min(k4_tma_blocks_per_sm, sizeof(S) == 4 ? 4 : 2); }
+        if (const char* b = getenv("RBA_MATVEC_BLOCKS_PER_SM")) k4_tma_blocks_per_sm = std::max(1, atoi(b));
       }
     }
 #undef TRY
@@ -397,7 +385,6 @@ struct Solver : rba_handle {
   size_t k4_smem_small = 0, k4_smem_tma = 0;
   bool use_tma = true;
   int k4_tma_blocks_per_sm = 2;
-  int dyn_blocks_per_sm = sizeof(S) == 4 ? 4 : 2;
 
   // ------------------------------------------------------------------------------------------
   // sum over the shards, in place, on the solver stream: peer-memory push exchange when the ranks have mapped each other's
@@ -408,7 +395,7 @@ struct Solver : rba_handle {
       ++c_seq;
       const int g = (int)std::max<size_t>(1, std::min<size_t>((size_t)sm_count, (count + 255) / 256));
       k_peer_push<S><<<g, 256, 0, stream>>>(pc, buf, (long long)count, c_seq & 1);
-      k_peer_sum<S><<<g, 256, 0, stream>>>(pc, buf, (long long)count, c_seq & 1, c_seq, d_flags);
+      k_peer_sum<S><<<g, 256, 0, stream>>>(pc, buf, (long long)count, c_seq & 1, c_seq, d_flags + 1);
       launches += 2;
       return RBA_OK;
     }
@@ -422,7 +409,7 @@ struct Solver : rba_handle {
     if (opt.nranks == 1) return RBA_OK;
     if (peer_ok) {
       ++s_seq;
-      k_peer_small<<<1, 64, 0, stream>>>(pc, d_red, nd, d_flags, 4, s_seq & 1, s_seq, d_flags);
+      k_peer_small<<<1, 64, 0, stream>>>(pc, d_red, nd, d_flags, 4, s_seq & 1, s_seq, d_flags + 1);
       ++launches;
       return RBA_OK;
     }
@@ -558,6 +545,7 @@ struct Solver : rba_handle {
     CU(cudaStreamSynchronize(stream));
     out->all_num_obs = (int64_t)llround(h_red[0]); out->all_error = h_red[1]; out->all_residual_sum = h_red[2];
     out->valid_num_obs = (int64_t)llround(h_red[3]); out->valid_error = h_red[4]; out->valid_residual_sum = h_red[5];
+    if (h_flags[1]) { g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
     out->is_numerically_valid = h_flags[0] ? 0 : 1;
     out->pad_ = 0;
     tm.residual_evaluation_time = elapsed(ev_error);
@@ -606,6 +594,7 @@ struct Solver : rba_handle {
     new_linearization_point = true;
     damping_valid = false;
     have_inc = false;
+    if (h_flags[1]) { g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
     if (h_flags[0]) { linearized = false; return RBA_NUMERICAL_FAILURE; }  // reference: CHECK abort (linearizor_qr.cpp:121-122)
     return RBA_OK;
   }
@@ -626,7 +615,6 @@ struct Solver : rba_handle {
 
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
   void matvec_launch(const S* xvec, const int* done) {
-    if (use_dyn) cudaMemsetAsync(d_queue, 0, 2 * sizeof(int), stream);  // a PCG solve that stopped early may have left claims behind
     matvec_kernels(xvec, done);
     k_cam_reduce<S><<<grid_for(n_op_items, 8, 8), 256, 0, stream>>>(D.yobs, op_slots, op_items, n_op_items, D.partial, done);
     ++launches;
@@ -649,11 +637,7 @@ struct Solver : rba_handle {
           D, d_items, 0, L.n_items_large, L.k4_scratch_per_warp, xvec, done);
       ++launches;
     }
-    if (nitems > L.n_items_large && use_dyn) {
-      const bool p = pdl && use_pdl && L.n_items_large == 0;
-      launch_ex(k_matvec_dyn<S, K4_WARPS, K4_NS, K4_STAGE>, sm_count * dyn_blocks_per_sm, K4_WARPS * 32, (size_t)K4_WARPS * K4_NS * K4_STAGE, p, 1,
-                D, (const ItemRec*)d_item_recs, L.n_items_large, nitems, d_queue, xvec, done, (int)p);
-    } else if (nitems > L.n_items_large) {
+    if (nitems > L.n_items_large) {
       if (use_tma) {
         launch_ex(k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>, grid_for(nitems - L.n_items_large, K4_WARPS, k4_tma_blocks_per_sm), K4_WARPS * 32,
                   k4_smem_tma, pdl && use_pdl && L.n_items_large == 0, 1, D, (const MatvecItem*)d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done,
@@ -728,7 +712,6 @@ struct Solver : rba_handle {
     // PCG (ref: cg/conjugate_gradient.hpp:113-298 ; linearizor_base.cpp:81-103)
     rc = start(ev_pcg); if (rc) return rc;
     CU(cudaMemsetAsync(d_state, 0, sizeof(PcgState), stream));
-    if (use_dyn) CU(cudaMemsetAsync(d_queue, 0, 2 * sizeof(int), stream));
     const int max_it = std::max(opt.max_linear_solver_iterations, 1);
     const int period = opt.residual_reset_period;
     const int chk = opt.pcg_check_period;
@@ -778,7 +761,10 @@ struct Solver : rba_handle {
       cg->reason = h_state[0].reason;
       cg->num_matvecs = h_state[0].iter + h_state[0].iter / period;
     }
-    if (h_state[0].reason == 99) g_err = "PCG: a peer rank did not publish its operator output in time (peer-memory all-reduce timed out)";
+    if (h_state[0].reason == 99) {
+      g_err = "PCG: a peer rank did not publish its operator output in time (peer-memory exchange timed out)";
+      return RBA_ERR_NCCL;
+    }
     return RBA_OK;
   }
 
@@ -812,6 +798,7 @@ struct Solver : rba_handle {
     tm.back_substitution_time = elapsed(ev_backsub);
     tm.update_cameras_time = elapsed(ev_update);
     tm.kernel_launches = launches - l0;
+    if (h_flags[1]) { g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
     S l = (S)h_red[0];
     int ret = RBA_OK;
     if (h_flags[0] || !std::isfinite((double)l)) { l = std::numeric_limits<S>::quiet_NaN(); ret = RBA_NUMERICAL_FAILURE; }
