@@ -27,7 +27,14 @@ def main():
     import rootba_b200 as rb
     from rootba_b200.synthetic import synth_bal
     # sequence-like visibility: every shard misses most cameras (the case the in-place all-reduce must get right)
-    arrays = synth_bal(120, 6000, 4.5, seed=17, locality=2.0, max_track=60)
+    arrays = synth_bal(300, 6000, 4.5, seed=17, locality=2.0, max_track=40)
+    # landmarks in order of their first camera: a shard (contiguous landmark range) then sees only part of the cameras
+    from rootba_b200.synthetic import BalArrays
+    n = np.diff(arrays.lm_off)
+    order = np.argsort(arrays.obs_cam[arrays.lm_off[:-1]], kind="stable")
+    off = np.concatenate([[0], np.cumsum(n[order])]).astype(np.int64)
+    idx = np.concatenate([np.arange(arrays.lm_off[l], arrays.lm_off[l + 1]) for l in order])
+    arrays = BalArrays(arrays.cams, arrays.lms[order].copy(), off, arrays.obs_cam[idx].copy(), arrays.obs_xy[idx].copy())
     bp = rb.BalProblem.from_arrays(arrays, dtype)
     so = rb.SolverOptions(device=local, rank=rank, nranks=world)
     lin = rb.LinearizorQR.create(bp, so)
