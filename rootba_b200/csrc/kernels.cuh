@@ -655,90 +655,6 @@ __device__ __forceinline__ void rot_apply(const Rot<S>& g, S& x, S& y) {
 //   block-diagonal Jp through their compact-WY form, one output element = 3 FMAs, written straight into
 //   the coalesced panel layout.
 // ------------------------------------------------------------------------------------------------
-// scratch geometry of k_linearize_qr (host mirrors it in Solver::init)
-__host__ __device__ inline int k1_group_stride(int n) { return 36 * n + ((n & 1) ? 0 : 4); }
-__host__ __device__ inline int k1_need(int n, int G) {
-  const int W = 32 / G;
-  return ((W * k1_group_stride(n) + 3) & ~3) + 28 * W * n + 64;
-}
-
-// Compact-WY application of Q^T = H2 H1 H0 to the block-diagonal Jp for the KPC column pairs k0 .. k0 + KPC - 1 of a lane
-// (ref: ipp:717-743, applyHouseholderOnTheLeft on every column).  Element (r, c) of Q^T Jp is  delta_r * a - V[r] . w_c
-// with w_c = T^T V^T a_c (3 numbers per column, kept in REGISTERS for all the lane's columns), so the panel is produced
-// row by row: one 16-byte shared-memory load of V[r] per row, 6 FMAs and one 8-byte store per column pair, and a warp
-// writes KP consecutive 256-byte (f32) segments = one whole panel row per step.  Rows 0..2 (Q1^T Jp) go to the q1u
-// staging buffer; the two rows that carry the original Jacobian entries of a column are patched afterwards.
-template <class S, int KPC>
-__device__ __forceinline__ void wy_apply(const S* sJ, const S* sV, S* sQ, const S (&tau)[3], S g10, S g20, S g21, int n, int G, int g, int j,
-                                         int ncols, int nrows, bool write, typename ST<S>::V2* prow0 /* ptile + lane */, int k0 = 0, int KP = KPC) {
-  using V2 = typename ST<S>::V2;
-  using V4 = typename ST<S>::V4;
-  S w[KPC][2][3];
-#pragma unroll
-  for (int kk = 0; kk < KPC; ++kk) {
-    const int k = k0 + kk;
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int c = 2 * j + 2 * G * k + v;
-      const bool vc = k < KP && c < ncols;
-      const int i = vc ? c / 9 : 0;
-      const int p = vc ? c - 9 * i : 0;
-      const S a0 = vc ? sJ[28 * i + p] : S(0), a1 = vc ? sJ[28 * i + 9 + p] : S(0);
-      const S* va = sV + 4 * (2 * i);
-      const S z0 = va[0] * a0 + va[4] * a1;
-      const S z1 = va[1] * a0 + va[5] * a1;
-      const S z2 = va[2] * a0 + va[6] * a1;
-      const S w0 = tau[0] * z0;
-      const S w1 = tau[1] * (z1 - g10 * w0);
-      const S w2 = tau[2] * (z2 - g20 * w0 - g21 * w1);
-      w[kk][v][0] = w0; w[kk][v][1] = w1; w[kk][v][2] = w2;
-      // rows 0..2 = Q1^T Jp (undamped) -> staging
-      if (vc) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const S sel = (r == 2 * i) ? a0 : ((r == 2 * i + 1) ? a1 : S(0));
-          sQ[28 * (g * n + i) + 9 * r + p] = sel - (w0 * sV[4 * r] + w1 * sV[4 * r + 1] + w2 * sV[4 * r + 2]);
-        }
-      }
-    }
-  }
-  if (!write) return;
-  // rows 3..2n-1 = Q2^T Jp
-  const size_t rstride = (size_t)KP * 32;
-  V2* pr = prow0 + (size_t)k0 * 32;
-#pragma unroll 2
-  for (int r = 3; r < nrows; ++r, pr += rstride) {
-    S v0, v1, v2;
-    if (sizeof(S) == 4) { const float4 t = *reinterpret_cast<const float4*>(sV + 4 * r); v0 = t.x; v1 = t.y; v2 = t.z; }
-    else { const double2 t = *reinterpret_cast<const double2*>(sV + 4 * r); v0 = t.x; v1 = t.y; v2 = sV[4 * r + 2]; }
-#pragma unroll
-    for (int kk = 0; kk < KPC; ++kk)
-      if (k0 + kk < KP)
-        pr[kk * 32] = mk2(-(w[kk][0][0] * v0 + w[kk][0][1] * v1 + w[kk][0][2] * v2), -(w[kk][1][0] * v0 + w[kk][1][1] * v1 + w[kk][1][2] * v2));
-  }
-  // patch: rows 2i and 2i+1 of a column also carry a0 / a1 (the lane re-writes its own elements)
-#pragma unroll
-  for (int kk = 0; kk < KPC; ++kk) {
-    const int k = k0 + kk;
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-      const int c = 2 * j + 2 * G * k + v;
-      if (k >= KP || c >= ncols) continue;
-      const int i = c / 9, p = c - 9 * i;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int r = 2 * i + q;
-        if (r >= 3) {
-          const S* vq = sV + 4 * r;
-          const S val = sJ[28 * i + 9 * q + p] - (w[kk][v][0] * vq[0] + w[kk][v][1] * vq[1] + w[kk][v][2] * vq[2]);
-          *(reinterpret_cast<S*>(prow0 + (size_t)(r - 3) * rstride + (size_t)k * 32) + v) = val;
-        }
-      }
-    }
-  }
-  (void)V4();
-}
-
 template <class S, bool GIVENS>
 __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scratch<S> sc, int* bad_flag) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -752,11 +668,10 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
     const int g = lane / G, j = lane - g * G;
     const bool active = g < T.nvalid;
     const int Wn = (32 / G) * n;
-    S* ws = scratch_ptr(sc, ws_smem, k1_need(n, G));
-    const int GS = k1_group_stride(n);  // per-landmark scratch stride: 36 n (+4): a multiple of 4 with GS / 4 odd, so the 16-byte
-                                        // broadcast reads of different groups in a quarter warp hit distinct banks
-    S* sJ = ws + (size_t)g * GS;      // [n][28]: jp row0 (9) | jp row1 (9) | jl row0 (3) | jl row1 (3) | r (2) | pad (2)
-    S* sV = sJ + 28 * n;              // [2n][4] Householder vectors (3 used; rows 16-byte aligned)
+    S* ws = scratch_ptr(sc, ws_smem, Wn * 60 + 64);
+    const int GS = 32 * n + 1;        // per-landmark scratch stride, odd => group-broadcast reads hit distinct banks
+    S* sJ = ws + (size_t)g * GS;      // [n][26]: jp row0 (9) | jp row1 (9) | jl row0 (3) | jl row1 (3) | r (2)
+    S* sV = sJ + 26 * n;              // [2n][3] Householder vectors
     S* sQ = ws + (((size_t)(32 / G) * GS + 3) & ~(size_t)3);  // [W*n][28] staging of the undamped Q1^T Jp rows
     const int slot0 = T.slot_base + g * n;
     const int sidx = T.lm_base + g;
@@ -768,7 +683,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
     __syncwarp();
     // ---- a. Jacobians of the observations (ref: ipp:106-140) ----
     for (int i = j; i < n; i += G) {
-      S* e = sJ + 28 * i;
+      S* e = sJ + 26 * i;
       bool wrote = false;
       if (active) {
         const int s = slot0 + i;
@@ -806,13 +721,13 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
       }
       if (!wrote)
 #pragma unroll
-        for (int c = 0; c < 28; ++c) e[c] = 0;
+        for (int c = 0; c < 26; ++c) e[c] = 0;
     }
     __syncwarp();
     // ---- b. scale_Jl_cols (ref: ipp:571-587) ----
     S cs[3] = {0, 0, 0};
     for (int i = j; i < n; i += G) {
-      const S* e = sJ + 28 * i + 18;
+      const S* e = sJ + 26 * i + 18;
 #pragma unroll
       for (int c = 0; c < 3; ++c) cs[c] += e[c] * e[c] + e[3 + c] * e[3 + c];
     }
@@ -823,7 +738,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
       jls[c] = S(1) / (eps + sqrt(cs[c]));
     }
     for (int i = j; i < n; i += G) {
-      S* e = sJ + 28 * i + 18;
+      S* e = sJ + 26 * i + 18;
 #pragma unroll
       for (int c = 0; c < 3; ++c) { e[c] *= jls[c]; e[3 + c] *= jls[c]; }
     }
@@ -835,19 +750,19 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
       S* jo = D.jp + 20 * sb;
       for (int e = lane; e < n * 20; e += 32) {
         const int i2 = e / 20, k = e - 20 * i2;
-        jo[e] = k < 18 ? src[28 * i2 + k] : S(0);
+        jo[e] = k < 18 ? src[26 * i2 + k] : S(0);
       }
       S* lo = D.jl + 6 * sb;
       for (int e = lane; e < n * 6; e += 32) {
         const int i2 = e / 6, k = e - 6 * i2;
-        lo[e] = src[28 * i2 + 18 + k];
+        lo[e] = src[26 * i2 + 18 + k];
       }
       S* ro = D.res + 2 * sb;
-      for (int e = lane; e < n * 2; e += 32) ro[e] = src[28 * (e >> 1) + 24 + (e & 1)];
+      for (int e = lane; e < n * 2; e += 32) ro[e] = src[26 * (e >> 1) + 24 + (e & 1)];
     }
     __syncwarp();
     // ---- c. Householder QR of A = [Jl | r] (2n x 4), rows rho = 2i + parity ----
-#define A_AT(rho, c) sJ[28 * ((rho) >> 1) + ((c) < 3 ? 18 + 3 * ((rho)&1) + (c) : 24 + ((rho)&1))]
+#define A_AT(rho, c) sJ[26 * ((rho) >> 1) + ((c) < 3 ? 18 + 3 * ((rho)&1) + (c) : 24 + ((rho)&1))]
     S tau[3] = {0, 0, 0};
     const int nrows = 2 * n;
     if constexpr (GIVENS) {
@@ -866,7 +781,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
               rot_apply(gr, x, y);  // applyOnTheLeft(m, m-1, gr)
               A_AT(m, c) = x; A_AT(m - 1, c) = y;
             }
-            sV[4 * m + k] = gr.c;
+            sV[3 * m + k] = gr.c;
             A_AT(m, k) = gr.s;
           }
         }
@@ -921,14 +836,14 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
             for (int c = 1; c <= 3; ++c) if (k + c <= 3) A_AT(rho, k + c) -= te * tmp[c - 1];
           }
         }
-        sV[4 * rho + k] = v;
+        sV[3 * rho + k] = v;
       }
       __syncwarp();
     }
     S g10 = 0, g20 = 0, g21 = 0;
     if constexpr (!GIVENS) {
       for (int rho = j; rho < nrows; rho += G) {
-        const S v0 = sV[4 * rho], v1 = sV[4 * rho + 1], v2 = sV[4 * rho + 2];
+        const S v0 = sV[3 * rho], v1 = sV[3 * rho + 1], v2 = sV[3 * rho + 2];
         g10 += v1 * v0; g20 += v2 * v0; g21 += v2 * v1;
       }
       g10 = group_sum(g10, G); g20 = group_sum(g20, G); g21 = group_sum(g21, G);
@@ -965,14 +880,14 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
           const int i = vc[v] ? c / 9 : 0;
           const int p = vc[v] ? c - 9 * i : 0;
           oi[v] = i; op[v] = p; r2i[v] = 2 * i;
-          a0[v] = vc[v] ? sJ[28 * i + p] : S(0);
-          a1[v] = vc[v] ? sJ[28 * i + 9 + p] : S(0);
+          a0[v] = vc[v] ? sJ[26 * i + p] : S(0);
+          a1[v] = vc[v] ? sJ[26 * i + 9 + p] : S(0);
           cur0[v] = (R == r2i[v] + 1) ? a1[v] : S(0);
         }
         V2* pk = ptile + (size_t)k * 32 + lane;
 #pragma unroll 1
         for (int t = R; t >= 1; --t) {
-          const Rot<S> g0{sV[4 * t], A_AT(t, 0)};
+          const Rot<S> g0{sV[3 * t], A_AT(t, 0)};
           S o0[2], o1[2] = {0, 0};
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
@@ -985,7 +900,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
             cur1[0] = o0[0]; cur1[1] = o0[1];
             continue;
           }
-          const Rot<S> g1{sV[4 * (t + 1) + 1], A_AT(t + 1, 1)};
+          const Rot<S> g1{sV[3 * (t + 1) + 1], A_AT(t + 1, 1)};
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
             S y = o0[v];
@@ -997,7 +912,7 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
             cur2[0] = o1[0]; cur2[1] = o1[1];
             continue;
           }
-          const Rot<S> g2{sV[4 * (t + 2) + 2], A_AT(t + 2, 2)};
+          const Rot<S> g2{sV[3 * (t + 2) + 2], A_AT(t + 2, 2)};
           S f[2];
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
@@ -1016,17 +931,65 @@ __global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scr
           }
       }
     }
-    if constexpr (!GIVENS) {
-      switch (KP) {
-        case 5: wy_apply<S, 5>(sJ, sV, sQ, tau, g10, g20, g21, n, G, g, j, ncols, nrows, active && o.write_panel, ptile + lane); break;
-        case 6: wy_apply<S, 6>(sJ, sV, sQ, tau, g10, g20, g21, n, G, g, j, ncols, nrows, active && o.write_panel, ptile + lane); break;
-        case 7: wy_apply<S, 7>(sJ, sV, sQ, tau, g10, g20, g21, n, G, g, j, ncols, nrows, active && o.write_panel, ptile + lane); break;
-        case 8: wy_apply<S, 8>(sJ, sV, sQ, tau, g10, g20, g21, n, G, g, j, ncols, nrows, active && o.write_panel, ptile + lane); break;
-        case 9: wy_apply<S, 9>(sJ, sV, sQ, tau, g10, g20, g21, n, G, g, j, ncols, nrows, active && o.write_panel, ptile + lane); break;
-        default:  // long tracks: the column pairs in chunks of 8
-          for (int k0 = 0; k0 < KP; k0 += 8)
-            wy_apply<S, 8>(sJ, sV, sQ, tau, g10, g20, g21, n, G, g, j, ncols, nrows, active && o.write_panel, ptile + lane, k0, KP);
-          break;
+#pragma unroll 1
+    for (int k = 0; k < (GIVENS ? 0 : KP); ++k) {
+      const int c0 = 2 * j + 2 * G * k;
+      S a0[2], a1[2], w0[2], w1[2], w2[2];
+      int r2i[2], oi[2], op[2];
+      bool vc[2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int c = c0 + v;
+        vc[v] = c < ncols;
+        const int i = vc[v] ? c / 9 : 0;
+        const int p = vc[v] ? c - 9 * i : 0;
+        oi[v] = i; op[v] = p; r2i[v] = 2 * i;
+        a0[v] = vc[v] ? sJ[26 * i + p] : S(0);
+        a1[v] = vc[v] ? sJ[26 * i + 9 + p] : S(0);
+        const S* va = sV + 3 * (2 * i);
+        const S z0 = va[0] * a0[v] + va[3] * a1[v];
+        const S z1 = va[1] * a0[v] + va[4] * a1[v];
+        const S z2 = va[2] * a0[v] + va[5] * a1[v];
+        w0[v] = tau[0] * z0;
+        w1[v] = tau[1] * (z1 - g10 * w0[v]);
+        w2[v] = tau[2] * (z2 - g20 * w0[v] - g21 * w1[v]);
+      }
+      // rows 0..2 = Q1^T Jp (undamped) -> staging
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const S v0 = sV[3 * r], v1 = sV[3 * r + 1], v2 = sV[3 * r + 2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const S sel = (r == r2i[v]) ? a0[v] : ((r == r2i[v] + 1) ? a1[v] : S(0));
+          if (vc[v]) sQ[28 * (g * n + oi[v]) + 9 * r + op[v]] = sel - (w0[v] * v0 + w1[v] * v1 + w2[v] * v2);
+        }
+      }
+      // rows 3..2n-1 = Q2^T Jp: out = -V[r] . w ; the two rows that carry the original Jacobian entries are patched below
+      if (active && o.write_panel) {
+        V2* pk = ptile + (size_t)k * 32 + lane;
+        const S nw00 = vc[0] ? -w0[0] : S(0), nw01 = vc[0] ? -w1[0] : S(0), nw02 = vc[0] ? -w2[0] : S(0);
+        const S nw10 = vc[1] ? -w0[1] : S(0), nw11 = vc[1] ? -w1[1] : S(0), nw12 = vc[1] ? -w2[1] : S(0);
+        const S* vp = sV + 9;
+#pragma unroll 4
+        for (int r = 3; r < nrows; ++r, vp += 3) {
+          const S v0 = vp[0], v1 = vp[1], v2 = vp[2];
+          pk[(size_t)(r - 3) * KP * 32] = mk2(nw00 * v0 + nw01 * v1 + nw02 * v2, nw10 * v0 + nw11 * v1 + nw12 * v2);
+        }
+        // patch: rows 2i and 2i+1 of each column also carry a0 / a1 (same lane re-writes its own element)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (!vc[v]) continue;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int r = r2i[v] + q;
+            if (r >= 3) {
+              const S* vq = sV + 3 * r;
+              const S val = (q == 0 ? a0[v] : a1[v]) - (w0[v] * vq[0] + w1[v] * vq[1] + w2[v] * vq[2]);
+              S* dst = reinterpret_cast<S*>(pk + (size_t)(r - 3) * KP * 32) + v;
+              *dst = val;
+            }
+          }
+        }
       }
     }
 #undef A_AT

@@ -304,7 +304,7 @@ struct Solver : rba_handle {
       long long need1 = 0, need2 = 0;
       for (const TileInfo& T : L.tiles) {
         const int Wn = (32 / T.G) * T.n;
-        need1 = std::max<long long>(need1, (long long)k1_need(T.n, T.G));
+        need1 = std::max<long long>(need1, (long long)Wn * 60 + 64);
         need2 = std::max<long long>(need2, (long long)stage2_need(T.n, T.G, T.KP));
       }
       auto setup = [&](Scratch<S>& sc, int cap, long long need, size_t& smem, int& blocks_per_sm, int& max_blocks) -> int {
@@ -377,7 +377,7 @@ struct Solver : rba_handle {
   static constexpr int K4_NS = RBA_K4_NS;        // TMA ring stages per warp
   static constexpr int K4_STAGE = RBA_K4_STAGE;  // bytes per stage (2 rows of an f32 KP=9 tile)
   static constexpr int TILE_WARPS = 4;
-  static constexpr int K1_CAP = 4288;   // scalars of shared memory per warp: linearize+QR needs k1_need(n, G) (<= 4288 for the standard tiles)
+  static constexpr int K1_CAP = 3904;   // scalars of shared memory per warp: linearize+QR needs 60 * W * n + 64 (= 3904 for the standard tiles)
   static constexpr int K2_CAP = 3072;   // stage 2 needs 3 * W * CS + 9 * W * n + 20 W + 8 (<= 3048 for the standard tiles)
   Scratch<S> k1_sc{}, k2_sc{};
   size_t k1_smem = 0, k2_smem = 0;
