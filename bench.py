@@ -73,21 +73,33 @@ class LMStepper:
         rec = {"lambda": float(self.lam), "solve": self.solves, "it": self.it + 1}
         terminated = False
         with np.errstate(all="ignore"):
+            fused = getattr(b, "fused", False)
+            lin_first = self.new_outer
             if self.new_outer:
                 self.ri = b.compute_error()
-                b.linearize()
+                if not fused:
+                    b.linearize()
                 self.new_outer = False
-            inc_ok = b.solve(float(self.lam))
+            if fused:  # rba_lm_step: [linearize] + solve + backup + apply + compute_error with one host synchronisation
+                fr = b.lm_step(float(self.lam), lin_first)
+                inc_ok = not fr["solve_failed"]
+            else:
+                inc_ok = b.solve(float(self.lam))
             rec["cg_iterations"] = b.cg_iterations()
             self.it += 1
             if not inc_ok:
+                if fused:
+                    b.restore()
                 self.lam = S(self.vee * self.lam); self.vee = S(self.vee * self.vee_factor)
                 rec["accepted"] = False
                 terminated = bool(self.lam > self.max_lambda)
             else:
-                b.backup()
-                l_diff = S(b.apply())
-                ri2 = b.compute_error()
+                if fused:
+                    l_diff, ri2 = S(fr["l_diff"]), fr["cost"]
+                else:
+                    b.backup()
+                    l_diff = S(b.apply())
+                    ri2 = b.compute_error()
                 ok = bool(np.isfinite(l_diff)) and ri2["is_numerically_valid"]
                 success = False
                 if ok:
@@ -115,7 +127,8 @@ class LMStepper:
 
 
 class GpuBackend:
-    """device-resident state and increment (what `value` measures)"""
+    """device-resident state and increment (what `value` measures); one host synchronisation per LM iteration (rba_lm_step)"""
+    fused = True
 
     def __init__(self, lin):
         self.lin = lin
@@ -128,6 +141,7 @@ class GpuBackend:
         self.lin.upload_state()
 
     def compute_error(self): return self.lin.compute_error()
+    def lm_step(self, lam, linearize_first): return self.lin.lm_step(lam, linearize_first)
     def linearize(self): self.lin.linearize()
     def solve(self, lam):
         self.lin.solve(lam, to_host=False)
@@ -142,6 +156,7 @@ class GpuE2EBackend(GpuBackend):
     """every step moves its inputs host->device from pinned memory and its results device->host through the
     reference-facing API: state up, increment down, increment up (apply takes a host vector like
     LinearizorQR::apply(VecX&&)), state + l_diff + ResidualInfo down."""
+    fused = False
 
     def __init__(self, lin):
         super().__init__(lin)

@@ -221,6 +221,22 @@ int32_t rba_solve_f64(rba_handle* h, double lambda, double* inc_out, rba_cg_summ
  * inc == NULL uses the device-resident increment of the last rba_solve. l_diff is NaN on failure. */
 int32_t rba_apply_f32(rba_handle* h, const float* inc, float* l_diff_out);
 int32_t rba_apply_f64(rba_handle* h, const double* inc, double* l_diff_out);
+/* One LM inner iteration of optimize_lm_ours (bal_bundle_adjustment.cpp:324-521) with a SINGLE host synchronisation
+ * (SURVEY 8f row 2): [rba_linearize when linearize_first] + rba_solve(lambda) + rba_backup + rba_apply with the
+ * device-resident increment + rba_compute_error, enqueued back to back.  Same kernels in the same order as the separate
+ * calls: bit-identical results.  The caller keeps the reference's accept / reject and lambda logic and calls rba_restore
+ * on a rejected step -- also when `solve_failed` is set (PCG FAILURE = the reference's non-finite increment, which it
+ * does not apply; here the step is applied on the device first and undone by the restore).
+ * Returns like rba_apply: RBA_NUMERICAL_FAILURE when l_diff is not finite (l_diff = NaN). */
+typedef struct {
+  rba_cg_summary cg;
+  double l_diff;              /* model cost change (Scalar precision, widened) */
+  rba_residual_info cost;     /* ResidualInfo after the step */
+  int32_t solve_failed;
+  int32_t pad_;
+} rba_lm_step_result;
+int32_t rba_lm_step_f32(rba_handle* h, int32_t linearize_first, float lambda, rba_lm_step_result* out);
+int32_t rba_lm_step_f64(rba_handle* h, int32_t linearize_first, double lambda, rba_lm_step_result* out);
 /* device timings of the last calls */
 int32_t rba_get_timings(const rba_handle* h, rba_stage_timings* out);
 

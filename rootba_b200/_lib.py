@@ -51,6 +51,10 @@ class CgSummary(C.Structure):
                 ("reason", C.c_int32)]
 
 
+class LmStepResult(C.Structure):
+    _fields_ = [("cg", CgSummary), ("l_diff", C.c_double), ("cost", ResidualInfo), ("solve_failed", C.c_int32), ("pad_", C.c_int32)]
+
+
 class StageTimings(C.Structure):
     _fields_ = [("stage1_time", C.c_double), ("stage2_time", C.c_double),
                 ("compute_preconditioner_time", C.c_double), ("solve_reduced_system_time", C.c_double),

@@ -52,6 +52,7 @@ struct rba_handle {
   virtual int linearize() = 0;
   virtual int solve(double lambda, void* inc_out, rba_cg_summary* cg) = 0;
   virtual int apply(const void* inc, void* l_diff_out, bool update_cameras) = 0;
+  virtual int lm_step(bool linearize_first, double lambda, rba_lm_step_result* out) = 0;
   virtual int get_timings(rba_stage_timings* out) const = 0;
   virtual int get_stats(rba_workload_stats* out) const = 0;
   virtual int get_scaling(void* scaling, void* diag2) = 0;
@@ -91,7 +92,7 @@ struct Solver : rba_handle {
   S* cams_bk = nullptr; S* lms_bk = nullptr;
   MatvecItem* d_items = nullptr;
   long long state_version = 0;     // bumped whenever cameras / landmarks change (set_state, apply, restore)
-  rba_residual_info error_cache{}; long long error_cache_version = -1; bool error_cache_valid = false;
+  rba_residual_info error_cache{}; long long error_cache_version = -1, error_enqueue_version = -1; bool error_cache_valid = false;
   int* d_csr_obs_slots = nullptr; ReduceItem* d_csr_obs_items = nullptr; int* d_csr_obs_item_ptr = nullptr;
   int* d_csr_y_slots = nullptr; ReduceItem* d_csr_y_items = nullptr; int* d_csr_y_item_ptr = nullptr;
   int n_obs_items = 0, n_y_items = 0;
@@ -296,8 +297,8 @@ struct Solver : rba_handle {
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_state, 1));
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
-    CU(cudaMallocHost((void**)&h_red, 8 * sizeof(double)));
-    CU(cudaMallocHost((void**)&h_flags, 4 * sizeof(int)));
+    CU(cudaMallocHost((void**)&h_red, 24 * sizeof(double)));
+    CU(cudaMallocHost((void**)&h_flags, 12 * sizeof(int)));
     // tile kernels (linearize+QR, stage 2): scratch in shared memory when the tile fits in the kernel's cap (scalars per
     // warp), else in a per-warp slice of a global buffer (very long tracks; slow but general)
     {
@@ -524,15 +525,14 @@ struct Solver : rba_handle {
 
   // ------------------------------------------------------------------------------------------
   // ref: solver/linearizor_base.cpp:59-67
-  int compute_error(rba_residual_info* out) override {
-    // The LM loop evaluates the cost at the end of an accepted step and again, unchanged state, before the next
-    // linearisation (the reference's own TODO, bal_bundle_adjustment.cpp:298-301): the evaluation is deterministic, so
-    // the second call returns the cached ResidualInfo without touching the GPU.
-    if (error_cache_valid && error_cache_version == state_version) {
-      *out = error_cache;
-      tm.residual_evaluation_time = 0.0;
-      return RBA_OK;
-    }
+  // Every entry point is split into an enqueue half (kernels + asynchronous copies into its OWN pinned slot) and a finish
+  // half (after a stream synchronisation): the public calls are enqueue + synchronise + finish, rba_lm_step strings the
+  // enqueue halves of a whole LM inner iteration together and synchronises once.
+  // pinned slots: h_red + 8 * slot, h_flags + 4 * slot;  slot 0 compute_error, 1 linearize, 2 apply
+  bool error_enqueued = false;
+  int compute_error_enqueue() {
+    error_enqueued = false;
+    if (error_cache_valid && error_cache_version == state_version) return RBA_OK;  // answered from the cache in finish
     int rc = start(ev_error); if (rc) return rc;
     CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
     k_error<S><<<EBLOCKS, 256, 0, stream>>>(D, ko, d_epart, d_flags);
@@ -542,20 +542,38 @@ struct Solver : rba_handle {
     CU(cudaMemcpyAsync(h_red, d_red, 6 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     rc = stop(ev_error); if (rc) return rc;
-    CU(cudaStreamSynchronize(stream));
+    error_enqueued = true;
+    error_enqueue_version = state_version;
+    return RBA_OK;
+  }
+  int compute_error_finish(rba_residual_info* out) {
+    // The LM loop evaluates the cost at the end of an accepted step and again, unchanged state, before the next
+    // linearisation (the reference's own TODO, bal_bundle_adjustment.cpp:298-301): the evaluation is deterministic, so
+    // the second call returns the cached ResidualInfo without touching the GPU.
+    if (!error_enqueued) {
+      *out = error_cache;
+      tm.residual_evaluation_time = 0.0;
+      return RBA_OK;
+    }
     out->all_num_obs = (int64_t)llround(h_red[0]); out->all_error = h_red[1]; out->all_residual_sum = h_red[2];
     out->valid_num_obs = (int64_t)llround(h_red[3]); out->valid_error = h_red[4]; out->valid_residual_sum = h_red[5];
     if (h_flags[1]) { g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
     out->is_numerically_valid = h_flags[0] ? 0 : 1;
     out->pad_ = 0;
     tm.residual_evaluation_time = elapsed(ev_error);
-    error_cache = *out; error_cache_version = state_version; error_cache_valid = true;
+    error_cache = *out; error_cache_version = error_enqueue_version; error_cache_valid = true;
     return RBA_OK;
+  }
+  int compute_error(rba_residual_info* out) override {
+    int rc = compute_error_enqueue(); if (rc) return rc;
+    if (error_enqueued) CU(cudaStreamSynchronize(stream));
+    return compute_error_finish(out);
   }
 
   // ref: solver/linearizor_qr.cpp:78-138 (staged: LinearizationQR::get_stage1, linearization_qr.hpp:634-712)
-  int linearize() override {
-    const long long l0 = launches;
+  long long lin_l0 = 0;
+  int linearize_enqueue() {
+    lin_l0 = launches;
     int rc = start(ev_stage1); if (rc) return rc;
     CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
     // pass A: squared column norms of the weighted pose Jacobians -> pose_jacobian_scaling_
@@ -584,19 +602,26 @@ struct Solver : rba_handle {
       if (want_blocks) { rc = precond_blocks(3, D.blocks0, nullptr, false); if (rc) return rc; }
     }
     rc = allreduce_scalars(0); if (rc) return rc;
-    CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(h_flags + 4, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     rc = stop(ev_stage1); if (rc) return rc;
-    CU(cudaStreamSynchronize(stream));
-    CU(cudaGetLastError());
-    tm.stage1_time = elapsed(ev_stage1);
-    tm.kernel_launches = launches - l0;
-    linearized = true;
+    linearized = true;  // provisional: linearize_finish withdraws it on a numerical failure
     new_linearization_point = true;
     damping_valid = false;
     have_inc = false;
-    if (h_flags[1]) { g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
-    if (h_flags[0]) { linearized = false; return RBA_NUMERICAL_FAILURE; }  // reference: CHECK abort (linearizor_qr.cpp:121-122)
     return RBA_OK;
+  }
+  int linearize_finish() {
+    CU(cudaGetLastError());
+    tm.stage1_time = elapsed(ev_stage1);
+    tm.kernel_launches = launches - lin_l0;
+    if (h_flags[4 + 1]) { linearized = false; g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
+    if (h_flags[4 + 0]) { linearized = false; return RBA_NUMERICAL_FAILURE; }  // reference: CHECK abort (linearizor_qr.cpp:121-122)
+    return RBA_OK;
+  }
+  int linearize() override {
+    int rc = linearize_enqueue(); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    return linearize_finish();
   }
 
   // per-camera 9x9 blocks: deterministic two-phase sum over the camera-major observation CSR (modes: see k_precond_partial)
@@ -688,10 +713,11 @@ struct Solver : rba_handle {
   }
 
   // ref: solver/linearizor_qr.cpp:140-265
-  int solve(double lambda_d, void* inc_out, rba_cg_summary* cg) override {
+  long long solve_l0 = 0;
+  int solve_enqueue(double lambda_d, void* inc_out) {
     if (!linearized) { g_err = "rba_solve called before a successful rba_linearize"; return RBA_ERR_STATE; }
     const S lambda = (S)lambda_d;
-    const long long l0 = launches;
+    solve_l0 = launches;
     tm.matvec_launches = 0;
     int rc = start(ev_stage2); if (rc) return rc;
     // stage 2: landmark damping + gradient (+ SCHUR_JACOBI blocks)
@@ -747,19 +773,21 @@ struct Solver : rba_handle {
     CU(cudaMemcpyAsync(&h_state[0], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
     if (inc_out) CU(cudaMemcpyAsync(inc_out, D.inc, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
     rc = stop(ev_pcg); if (rc) return rc;
-    CU(cudaStreamSynchronize(stream));
-    CU(cudaGetLastError());
     have_inc = true;
     new_linearization_point = false;
+    return RBA_OK;
+  }
+  int solve_finish(rba_cg_summary* cg) {
+    CU(cudaGetLastError());
     tm.stage2_time = elapsed(ev_stage2);
     tm.compute_preconditioner_time = elapsed(ev_precond);
     tm.solve_reduced_system_time = elapsed(ev_pcg);
-    tm.kernel_launches = launches - l0;
+    tm.kernel_launches = launches - solve_l0;
     if (cg) {
       cg->termination_type = h_state[0].term;
       cg->num_iterations = h_state[0].iter;
       cg->reason = h_state[0].reason;
-      cg->num_matvecs = h_state[0].iter + h_state[0].iter / period;
+      cg->num_matvecs = h_state[0].iter + h_state[0].iter / opt.residual_reset_period;
     }
     if (h_state[0].reason == 99) {
       g_err = "PCG: a peer rank did not publish its operator output in time (peer-memory exchange timed out)";
@@ -767,11 +795,17 @@ struct Solver : rba_handle {
     }
     return RBA_OK;
   }
+  int solve(double lambda_d, void* inc_out, rba_cg_summary* cg) override {
+    int rc = solve_enqueue(lambda_d, inc_out); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    return solve_finish(cg);
+  }
 
   // ref: solver/linearizor_qr.cpp:267-291
-  int apply(const void* inc_host, void* l_diff_out, bool update_cameras) override {
+  long long apply_l0 = 0;
+  int apply_enqueue(const void* inc_host, bool update_cameras) {
     if (!linearized || !damping_valid) { g_err = "rba_apply / rba_back_substitute need rba_linearize + rba_solve first"; return RBA_ERR_STATE; }
-    const long long l0 = launches;
+    apply_l0 = launches;
     ++state_version;
     if (inc_host) CU(cudaMemcpyAsync(D.inc, inc_host, (size_t)9 * nc * sizeof(S), cudaMemcpyHostToDevice, stream));
     else if (!have_inc) { g_err = "no device-resident increment"; return RBA_ERR_STATE; }
@@ -791,19 +825,51 @@ struct Solver : rba_handle {
       ++launches;
     }
     rc = stop(ev_update); if (rc) return rc;
-    CU(cudaMemcpyAsync(h_red, d_red, sizeof(double), cudaMemcpyDeviceToHost, stream));
-    CU(cudaMemcpyAsync(h_flags, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CU(cudaStreamSynchronize(stream));
+    CU(cudaMemcpyAsync(h_red + 16, d_red, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(h_flags + 8, d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    return RBA_OK;
+  }
+  int apply_finish(void* l_diff_out) {
     CU(cudaGetLastError());
     tm.back_substitution_time = elapsed(ev_backsub);
     tm.update_cameras_time = elapsed(ev_update);
-    tm.kernel_launches = launches - l0;
-    if (h_flags[1]) { g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
-    S l = (S)h_red[0];
+    tm.kernel_launches = launches - apply_l0;
+    if (h_flags[8 + 1]) { g_err = "a peer rank did not take part in a cross-shard reduction in time (peer-memory exchange timed out)"; return RBA_ERR_NCCL; }
+    S l = (S)h_red[16];
     int ret = RBA_OK;
-    if (h_flags[0] || !std::isfinite((double)l)) { l = std::numeric_limits<S>::quiet_NaN(); ret = RBA_NUMERICAL_FAILURE; }
+    if (h_flags[8 + 0] || !std::isfinite((double)l)) { l = std::numeric_limits<S>::quiet_NaN(); ret = RBA_NUMERICAL_FAILURE; }
     *(S*)l_diff_out = l;
     return ret;
+  }
+  int apply(const void* inc_host, void* l_diff_out, bool update_cameras) override {
+    int rc = apply_enqueue(inc_host, update_cameras); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    return apply_finish(l_diff_out);
+  }
+
+  // One LM inner iteration with ONE host synchronisation: [linearize] + solve(lambda) + backup + apply with
+  // the device-resident increment + compute_error, the enqueue halves back to back.  Same kernels in the same order as the
+  // separate calls, hence bit-identical results.  The reference skips apply when the increment is not finite
+  // (bal_bundle_adjustment.cpp:360-399); here the step is applied on the device regardless and the caller restores the
+  // backup when `solve_failed` is set (the backup is taken inside).
+  int lm_step(bool linearize_first, double lambda, rba_lm_step_result* out) override {
+    std::memset(out, 0, sizeof(*out));
+    int rc;
+    if (linearize_first) { rc = linearize_enqueue(); if (rc) return rc; }
+    rc = solve_enqueue(lambda, nullptr); if (rc) return rc;
+    rc = backup(); if (rc) return rc;
+    rc = apply_enqueue(nullptr, true); if (rc) return rc;
+    rc = compute_error_enqueue(); if (rc) return rc;
+    CU(cudaStreamSynchronize(stream));
+    if (linearize_first) { rc = linearize_finish(); if (rc) return rc; }  // numerical failure of the linearisation: as rba_linearize
+    rc = solve_finish(&out->cg); if (rc) return rc;
+    out->solve_failed = out->cg.termination_type == 2 ? 1 : 0;  // FAILURE: the increment is not usable (reference: non-finite inc)
+    S l = 0;
+    rc = apply_finish(&l);
+    if (rc < 0) return rc;
+    out->l_diff = (double)l;
+    int rc2 = compute_error_finish(&out->cost); if (rc2) return rc2;
+    return rc;  // RBA_NUMERICAL_FAILURE when l_diff is not finite (as rba_apply)
   }
 
   int get_timings(rba_stage_timings* out) const override { *out = tm; out->kernel_launches = launches; return RBA_OK; }
@@ -1112,6 +1178,8 @@ int32_t rba_solve_f32(rba_handle* h, float lambda, float* inc, rba_cg_summary* c
 int32_t rba_solve_f64(rba_handle* h, double lambda, double* inc, rba_cg_summary* cg) { CHECK_TYPE(h, 8); return h->solve(lambda, inc, cg); }
 int32_t rba_apply_f32(rba_handle* h, const float* inc, float* l) { CHECK_TYPE(h, 4); return h->apply(inc, l, true); }
 int32_t rba_apply_f64(rba_handle* h, const double* inc, double* l) { CHECK_TYPE(h, 8); return h->apply(inc, l, true); }
+int32_t rba_lm_step_f32(rba_handle* h, int32_t linearize_first, float lambda, rba_lm_step_result* out) { CHECK_TYPE(h, 4); return h->lm_step(linearize_first != 0, lambda, out); }
+int32_t rba_lm_step_f64(rba_handle* h, int32_t linearize_first, double lambda, rba_lm_step_result* out) { CHECK_TYPE(h, 8); return h->lm_step(linearize_first != 0, lambda, out); }
 int32_t rba_back_substitute_f32(rba_handle* h, const float* inc, float* l) { CHECK_TYPE(h, 4); return h->apply(inc, l, false); }
 int32_t rba_back_substitute_f64(rba_handle* h, const double* inc, double* l) { CHECK_TYPE(h, 8); return h->apply(inc, l, false); }
 int32_t rba_get_timings(const rba_handle* h, rba_stage_timings* out) { return h->get_timings(out); }

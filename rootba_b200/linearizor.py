@@ -20,8 +20,8 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import (CgSummary, ProblemView, RbaError, ResidualInfo, SolverOpts, StageTimings, WorkloadStats, check,
-                   struct_to_dict)
+from ._lib import (CgSummary, LmStepResult, ProblemView, RbaError, ResidualInfo, SolverOpts, StageTimings, WorkloadStats,
+                   check, struct_to_dict)
 
 
 @dataclasses.dataclass
@@ -262,6 +262,19 @@ class LinearizorQR:
             t = self.timings()
             self.it_summary.update(back_substitution_time=t["back_substitution_time"], update_cameras_time=t["update_cameras_time"])
         return float(l.value)
+
+    def lm_step(self, lam: float, linearize_first: bool) -> dict:
+        """one LM inner iteration with a single host synchronisation (rba_lm_step): [linearize] + solve + backup + apply +
+        compute_error.  Returns the pieces optimize_lm_ours needs; the caller restores on a rejected / failed step."""
+        r = LmStepResult()
+        check(getattr(_lib.lib(), f"rba_lm_step_{self.sfx}")(self.h, int(linearize_first), self.S(lam), C.byref(r)),
+              allow_numerical_failure=True)
+        self.last_cg = r.cg
+        ri = r.cost
+        return {"solve_failed": bool(r.solve_failed), "l_diff": float(r.l_diff),
+                "cost": {"all": {"num_obs": ri.all_num_obs, "error": ri.all_error, "residual_sum": ri.all_residual_sum},
+                         "valid": {"num_obs": ri.valid_num_obs, "error": ri.valid_error, "residual_sum": ri.valid_residual_sum},
+                         "is_numerically_valid": bool(ri.is_numerically_valid)}}
 
     # ---- LinearizationQR-level access (tests) ----
     def timings(self) -> dict:

@@ -311,6 +311,46 @@ def test_full_size_properties():
     lin.close()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lm_step_fused_equals_separate_calls(small_problem, dtype):
+    """rba_lm_step ([linearize] + solve + backup + apply + compute_error, ONE host synchronisation) gives
+    bit-identical results to the separate entry points, over accepted and rejected (restored) steps"""
+    import rootba_b200 as rb
+    so = rb.SolverOptions()
+    bpa, bpb = rb.BalProblem.from_arrays(small_problem, dtype), rb.BalProblem.from_arrays(small_problem, dtype)
+    a, b = rb.LinearizorQR.create(bpa, so), rb.LinearizorQR.create(bpb, so)
+    lam = 1e-4
+    new_point = True
+    for it in range(5):
+        reject = it == 2  # exercise restore in the middle
+        if new_point:
+            ea, eb = a.compute_error(), b.compute_error()
+            assert ea == eb
+            a.linearize()
+        a.solve(lam, to_host=False)
+        bpa.backup()
+        l_a = a.apply(None)
+        e_a = a.compute_error()
+        r = b.lm_step(lam, new_point)
+        assert not r["solve_failed"]
+        assert (l_a == r["l_diff"]) or (np.isnan(l_a) and np.isnan(r["l_diff"]))
+        assert e_a == r["cost"]
+        assert a.last_cg.num_iterations == b.last_cg.num_iterations and a.last_cg.termination_type == b.last_cg.termination_type
+        if reject:
+            bpa.restore(); bpb.restore()
+            lam *= 4
+            new_point = False
+        else:
+            lam /= 3
+            new_point = True
+    a.download_state(); b.download_state()
+    assert np.array_equal(bpa.cams, bpb.cams) and np.array_equal(bpa.lms, bpb.lms)
+    # the cost before a new linearisation point is answered from the cache (no kernel launch), bit-identical
+    l0 = b.timings()["kernel_launches"]
+    assert b.compute_error() == r["cost"] and b.timings()["kernel_launches"] == l0
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("config,dtype,kw", [
     ("ladybug-1723", np.float32, {}),                                      # BASELINE configs[1]
     ("trafalgar-257", np.float64, {"preconditioner_type": "JACOBI"}),      # BASELINE configs[2]
