@@ -186,6 +186,12 @@ int32_t rba_bal_load(const char* path, int32_t normalize, double scale, int32_t 
  * landmark is closer than `threshold` in front of the camera, then the landmarks left with fewer than 2 observations
  * (landmark indices are compacted).  Call after rba_bal_load, before rba_bal_dims / rba_bal_copy; threshold <= 0: no-op. */
 int32_t rba_bal_filter_obs(rba_bal_file* f, double threshold);
+/* BalProblem::perturb (bal_problem.cpp:507-554; BalDatasetOptions rotation_sigma / translation_sigma / point_sigma /
+ * random_seed, default seed 38401): Gaussian perturbation of the camera centres (world frame), the camera rotations
+ * (left-multiplied exp) and the landmarks, drawn from one std::default_random_engine exactly as the reference draws them
+ * (same random stream when the reference is built against libstdc++).  Call after rba_bal_load (which normalises) and
+ * before rba_bal_filter_obs -- the order of load_normalized_bal_problem (bal_problem.cpp:813-826).  seed < 0: random device. */
+int32_t rba_bal_perturb(rba_bal_file* f, double rotation_sigma, double translation_sigma, double point_sigma, int32_t seed);
 /* sizes, to allocate the arrays for rba_bal_copy */
 int32_t rba_bal_dims(const rba_bal_file* f, int32_t* num_cameras, int32_t* num_landmarks, int64_t* num_observations);
 /* cams [10*Nc] (qx,qy,qz,qw,t,f,k1,k2 = Camera::params(), bal_problem.hpp:84-89), lms [3*Nl], lm_obs_offset [Nl+1],

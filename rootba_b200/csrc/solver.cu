@@ -1056,6 +1056,11 @@ int32_t rba_bal_filter_obs(rba_bal_file* f, double threshold) {
   f->p.filter_obs(threshold);
   return RBA_OK;
 }
+int32_t rba_bal_perturb(rba_bal_file* f, double rotation_sigma, double translation_sigma, double point_sigma, int32_t seed) {
+  if (!f || rotation_sigma < 0 || translation_sigma < 0 || point_sigma < 0) { rba::g_err = "bad arguments"; return RBA_ERR_INVALID_ARGUMENT; }  // reference: CHECK_GE
+  f->p.perturb(rotation_sigma, translation_sigma, point_sigma, seed);
+  return RBA_OK;
+}
 int32_t rba_bal_dims(const rba_bal_file* f, int32_t* nc, int32_t* nl, int64_t* nobs) {
   if (!f) return RBA_ERR_INVALID_ARGUMENT;
   if (nc) *nc = f->p.nc;

@@ -29,6 +29,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <random>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -176,6 +177,47 @@ class BalProblemSoA {
       for (int a = 0; a < 3; ++a) ctr[a] = scale * (ctr[a] - median[a]);
       for (int a = 0; a < 3; ++a) c[4 + a] = -(R[3 * a] * ctr[0] + R[3 * a + 1] * ctr[1] + R[3 * a + 2] * ctr[2]);
     }
+  }
+
+  // ref: bal_problem.cpp:507-554 BalProblem::perturb (+ perturbation<T, N>, :105-114): camera centre in world coordinates
+  // += N(0, translation_sigma), rotation <- exp(N(0, rotation_sigma)) * rotation, landmark += N(0, landmark_sigma); one
+  // std::default_random_engine seeded with `seed` (seed < 0: std::random_device), a FRESH std::normal_distribution<double>
+  // per 3-vector exactly like the reference -- with libstdc++ (what a GCC build of the reference links) the random stream
+  // is therefore the reference's.  Runs in double before the cast to Scalar (bal_problem.cpp:820-826).
+  void perturb(double rotation_sigma, double translation_sigma, double landmark_sigma, int seed) {
+    static_assert(std::is_same<Scalar, double>::value, "perturb runs on the double problem, like the reference pipeline");
+    std::default_random_engine eng = seed < 0 ? std::default_random_engine{std::random_device{}()}
+                                              : std::default_random_engine{static_cast<std::default_random_engine::result_type>(seed)};
+    auto perturbation = [&](double sigma, double* v) {
+      std::normal_distribution<double> normal;
+      for (int i = 0; i < 3; ++i) v[i] = 0.0 + normal(eng) * sigma;
+    };
+    if (rotation_sigma > 0 || translation_sigma > 0) {
+      for (int i = 0; i < nc; ++i) {
+        Scalar* c = cams.data() + (size_t)CAM_STATE_SIZE * i;
+        if (translation_sigma > 0) {  // T_w_c.translation() += d ; T_c_w = T_w_c^-1  (rotation unchanged)
+          Scalar R[9], ctr[3], d[3];
+          quat_to_rot(c, R);
+          for (int a = 0; a < 3; ++a) ctr[a] = -(R[a] * c[4] + R[3 + a] * c[5] + R[6 + a] * c[6]);
+          perturbation(translation_sigma, d);
+          for (int a = 0; a < 3; ++a) ctr[a] += d[a];
+          for (int a = 0; a < 3; ++a) c[4 + a] = -(R[3 * a] * ctr[0] + R[3 * a + 1] * ctr[1] + R[3 * a + 2] * ctr[2]);
+        }
+        if (rotation_sigma > 0) {     // so3 <- exp(w) * so3 (translation unchanged, as the reference sets only .so3())
+          double w[3], q[4], qn[4];
+          perturbation(rotation_sigma, w);
+          detail::so3_exp(w, q);
+          detail::quat_mul(q, c, qn);
+          for (int a = 0; a < 4; ++a) c[a] = qn[a];
+        }
+      }
+    }
+    if (landmark_sigma > 0)
+      for (int i = 0; i < nl; ++i) {
+        double d[3];
+        perturbation(landmark_sigma, d);
+        for (int a = 0; a < 3; ++a) lms[3 * (size_t)i + a] += d[a];
+      }
   }
 
   // ref: bal_problem.cpp:471-505: drop observations with depth (z of T_c_w * p_w) below the threshold, then landmarks with

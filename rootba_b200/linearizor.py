@@ -86,13 +86,17 @@ class BalProblem:
 
     @classmethod
     def load_bal(cls, path: str, dtype=np.float64, normalize: bool = True, scale: float = 100.0, num_threads: int = 0,
-                 init_depth_threshold: float = 0.0) -> "BalProblem":
+                 init_depth_threshold: float = 0.0, rotation_sigma: float = 0.0, translation_sigma: float = 0.0,
+                 point_sigma: float = 0.0, random_seed: int = 38401) -> "BalProblem":
         """load_normalized_bal_problem (bal/bal_problem.cpp:773-852) through the library's multi-threaded BAL parser
         (rba_bal_load): load + normalise in double, then cast to dtype."""
         L = _lib.lib()
         f = C.c_void_p()
         check(L.rba_bal_load(os.fsencode(path), int(normalize), C.c_double(scale), int(num_threads), C.byref(f)))
         try:
+            if rotation_sigma > 0 or translation_sigma > 0 or point_sigma > 0:  # BalProblem::perturb (bal_problem.cpp:507-554, :820-822)
+                check(L.rba_bal_perturb(f, C.c_double(rotation_sigma), C.c_double(translation_sigma), C.c_double(point_sigma),
+                                        C.c_int32(random_seed)))
             if init_depth_threshold > 0:  # BalDatasetOptions::init_depth_threshold -> filter_obs (bal_problem.cpp:471-505, :826)
                 check(L.rba_bal_filter_obs(f, C.c_double(init_depth_threshold)))
             nc, nl, nobs = C.c_int32(), C.c_int32(), C.c_int64()
