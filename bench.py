@@ -567,7 +567,7 @@ def bench_ours(args):
             n1 = {"value": 1e3 * d1 / args.steps, "unit": "ms/LM-iter", "n_gpus": 1,
                   "what": "the same workload, protocol and trajectory on rank 0's GPU alone, measured in this run",
                   "pcg_us_per_iteration": 1e6 * ph1["solve_reduced_system_time"] / max(cg1, 1), "operator_us_per_launch": 1e6 * mv1,
-                  "final_cost": trajectory_fields(st1)["final_cost"]}
+                  "final_cost": trajectory_fields(st1)["final_cost"], "cg_iterations": trajectory_fields(st1)["cg_iterations"]}
             lin1.close()
         barrier()
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
