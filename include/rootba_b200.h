@@ -87,7 +87,13 @@ typedef struct {
                                               default), 1 = through the orthogonality identities Jp^T r - Q1d^T (Q1^T r)_d and
                                               Jp^T Jp - Q1d^T Q1d (O(n) per landmark, but they cancel: float64 only).  With
                                               operator_form = 1 no panels exist and form 1 is used. */
-  int32_t reserved[4];
+  int32_t solver_type;                     /* SolverOptions::solver_type (:63-76): 0 = SQUARE_ROOT (LinearizorQR, default), 1 = SCHUR_COMPLEMENT
+                                              (LinearizorSC, solver/linearizor_sc.cpp: landmark eliminated through the normal equations,
+                                              PCG on the reduced camera system), 2 = POWER_SCHUR_COMPLEMENT (LinearizorPowerSC,
+                                              solver/linearizor_power_sc.cpp: power-series solve, sc/linearization_power_sc.hpp:130-160;
+                                              one GPU).  Types 1 and 2 store no Q2 panels; same entry points, same protocol. */
+  int32_t power_order;                     /* :270 ; maximum number of terms of the power series (0 -> 20) */
+  int32_t reserved[2];
 } rba_solver_opts;
 
 /* ResidualInfo (bal/residual_info.hpp:59-89) */

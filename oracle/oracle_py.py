@@ -210,6 +210,39 @@ class Oracle:
         rows = [dict(zip(LOG_COLUMNS, log[i])) for i in range(n)]
         return rows, term.value
 
+    # --- LinearizorSC / LinearizorPowerSC (solver/linearizor_sc.cpp, solver/linearizor_power_sc.cpp) ---
+    def scl_linearize(self):
+        self._f("scl_linearize")(self.h)
+
+    def scl_get_scaling(self):
+        s = self._vec(9 * self.nc)
+        self._f("scl_get_scaling")(self.h, _p(s))
+        return s
+
+    def scl_solve(self, lam):
+        inc, b, inv = self._vec(9 * self.nc), self._vec(9 * self.nc), self._vec(81 * self.nc)
+        it, term = C.c_int(), C.c_int()
+        self._f("scl_solve")(self.h, self.S(lam), _p(inc), _p(b), _p(inv), C.byref(it), C.byref(term))
+        return inc, {"b": b, "inv_blocks": inv.reshape(self.nc, 9, 9), "cg_iterations": it.value, "cg_termination": term.value}
+
+    def scl_power_solve(self, lam, power_order=20, q_tolerance=0.1):
+        inc, b = self._vec(9 * self.nc), self._vec(9 * self.nc)
+        it, term = C.c_int(), C.c_int()
+        self._f("scl_power_solve")(self.h, self.S(lam), C.c_int(power_order), self.S(q_tolerance), _p(inc), _p(b), C.byref(it), C.byref(term))
+        return inc, {"b": b, "power_order": it.value, "termination": term.value}
+
+    def scl_e0(self, lam, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        y = self._vec(9 * self.nc)
+        self._f("scl_e0")(self.h, self.S(lam), _p(x), _p(y))
+        return y
+
+    def scl_apply(self, inc) -> float:
+        inc = np.ascontiguousarray(inc, dtype=self.dtype)
+        l = self.S(0)
+        self._f("scl_apply")(self.h, _p(inc), C.byref(l))
+        return float(l.value)
+
     # --- Schur complement cross-check ---
     def sc_linearize(self):
         d = self._vec(9 * self.nc)

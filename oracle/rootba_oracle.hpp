@@ -42,6 +42,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <functional>
 #include <vector>
 
 #ifdef _OPENMP
@@ -900,7 +901,9 @@ struct Problem {
 
   // ref: cg/conjugate_gradient.hpp:113-298 driven by solver/linearizor_base.cpp:81-103
   // returns iterations ; termination in last_cg_termination
+  std::function<void(const S*, S*)> op_override;  // Schur-complement solvers: H x through the SC landmark blocks
   int pcg(const std::vector<S>& bref, const std::vector<S>& inv_blocks, std::vector<S>& xref) {
+    auto right_multiply = [&](const S* xin, S* yout) { if (op_override) op_override(xin, yout); else this->right_multiply(xin, yout); };
     const size_t N = (size_t)9 * nc;
     int num_iterations = 0;
     last_cg_termination = 0;
@@ -1187,6 +1190,125 @@ struct Problem {
       l_diff -= acc;
       for (int d = 0; d < 3; ++d) lms_out[3 * (size_t)l + d] += inc[d] * B.Jl_col_scale[d];
     }
+    return l_diff;
+  }
+
+  // ---------------- LinearizorSC / LinearizorPowerSC (ref: solver/linearizor_sc.cpp, solver/linearizor_power_sc.cpp) -----------
+  std::vector<SCBlock> scl;             // the linearisation of the SC solvers
+  std::vector<S> sc_scaling;            // pose_jacobian_scaling_
+  S sc_lambda = 0;
+  int last_power_order = 0, last_power_termination = 0;
+  // linearize(): linearize_problem + get_Jp_diag2 + scale_Jl_cols + Jacobi scaling (linearizor_sc.cpp:78-110); the pose
+  // Jacobians are scaled here once (the reference does it in the first solve(), :128-131 -- same numbers)
+  void sc_linearizor_linearize() {
+    std::vector<S> d2;
+    sc_linearize(scl, d2);
+    sc_scaling.resize(d2.size());
+    for (size_t k = 0; k < d2.size(); ++k) sc_scaling[k] = S(1) / (jacobi_eps() + std::sqrt(d2[k]));
+    sc_scale_Jp(scl, sc_scaling.data());
+  }
+  // LinearizorSC::solve (linearizor_sc.cpp:112-204): H_pp, b_p (sc/linearization_sc.hpp get_Hb), SCHUR_JACOBI block
+  // preconditioner from the diagonal blocks of H_pp, PCG (LinearizorBase::pcg)
+  void sc_linearizor_solve(S lambda, std::vector<S>& inc, std::vector<S>* b_out = nullptr, std::vector<S>* inv_out = nullptr) {
+    sc_lambda = lambda;
+    const size_t N = (size_t)9 * nc;
+    std::vector<S> b, diag, y, zero(N, S(0));
+    sc_get_Hb(scl, lambda, lambda, b, diag, zero.data(), y);
+    std::vector<S> inv((size_t)81 * nc);
+    for (int c = 0; c < nc; ++c) invert_block9(diag.data() + (size_t)81 * c, nullptr, inv.data() + (size_t)81 * c);
+    op_override = [&](const S* xin, S* yout) {
+      std::vector<S> b2, d2, y2;
+      sc_get_Hb(scl, lambda, lambda, b2, d2, xin, y2);
+      std::copy(y2.begin(), y2.end(), yout);
+    };
+    inc.assign(N, S(0));
+    last_cg_iterations = pcg(b, inv, inc);
+    op_override = nullptr;
+    if (b_out) *b_out = b;
+    if (inv_out) *inv_out = inv;
+  }
+  // E_0 x = Jp^T Jl Hll^-1 Jl^T Jp x  (sc/linearization_power_sc.hpp:261-287)
+  void sc_right_mul_e0(S lambda, const S* x, S* out) const {
+    std::fill(out, out + (size_t)9 * nc, S(0));
+    for (int l = 0; l < nl; ++l) {
+      const int n = (int)(lm_off[l + 1] - lm_off[l]);
+      const auto& B = scl[l];
+      S Hi[9];
+      sc_Hll_inv(B, n, lambda, Hi);
+      S s[3] = {0, 0, 0};
+      for (int j = 0; j < n; ++j) {
+        const S* xj = x + (size_t)9 * obs_cam[lm_off[l] + j];
+        for (int rr = 0; rr < 2; ++rr) {
+          S acc = 0;
+          for (int c = 0; c < 9; ++c) acc += B.Jp[18 * j + 9 * rr + c] * xj[c];
+          for (int a = 0; a < 3; ++a) s[a] += B.Jl[6 * j + 3 * rr + a] * acc;
+        }
+      }
+      S His[3];
+      for (int a = 0; a < 3; ++a) His[a] = Hi[3 * a] * s[0] + Hi[3 * a + 1] * s[1] + Hi[3 * a + 2] * s[2];
+      for (int i = 0; i < n; ++i) {
+        S* o = out + (size_t)9 * obs_cam[lm_off[l] + i];
+        for (int rr = 0; rr < 2; ++rr) {
+          const S t = B.Jl[6 * i + 3 * rr] * His[0] + B.Jl[6 * i + 3 * rr + 1] * His[1] + B.Jl[6 * i + 3 * rr + 2] * His[2];
+          for (int c = 0; c < 9; ++c) o[c] += B.Jp[18 * i + 9 * rr + c] * t;
+        }
+      }
+    }
+  }
+  // LinearizorPowerSC::solve (linearizor_power_sc.cpp:112-167) = prepare_Hb + the power series of
+  // LinearizationPowerSC::solve (sc/linearization_power_sc.hpp:92-160)
+  void power_sc_linearizor_solve(S lambda, int power_order, S q_tolerance, std::vector<S>& accum, std::vector<S>* b_out = nullptr) {
+    sc_lambda = lambda;
+    const size_t N = (size_t)9 * nc;
+    // prepare_Hb: b_p as in the SC solver; Hpp = sum Jp_i^T Jp_i (+ lambda) inverted per camera
+    std::vector<S> b, diag, y, zero(N, S(0));
+    sc_get_Hb(scl, lambda, S(0), b, diag, zero.data(), y);
+    std::vector<S> Hpp((size_t)81 * nc, S(0)), Hinv((size_t)81 * nc);
+    for (int l = 0; l < nl; ++l) {
+      const int n = (int)(lm_off[l + 1] - lm_off[l]);
+      for (int i = 0; i < n; ++i) {
+        S* Dc = Hpp.data() + (size_t)81 * obs_cam[lm_off[l] + i];
+        const S* J = scl[l].Jp.data() + 18 * i;
+        for (int a = 0; a < 9; ++a) for (int c = 0; c < 9; ++c) Dc[9 * a + c] += J[a] * J[c] + J[9 + a] * J[9 + c];
+      }
+    }
+    S dg[9];
+    for (int d = 0; d < 9; ++d) dg[d] = lambda;
+    for (int c = 0; c < nc; ++c) invert_block9(Hpp.data() + (size_t)81 * c, dg, Hinv.data() + (size_t)81 * c);
+    auto mul_inv = [&](const std::vector<S>& v, std::vector<S>& out) {
+      for (int c = 0; c < nc; ++c)
+        for (int i = 0; i < 9; ++i) {
+          S acc = 0;
+          for (int j = 0; j < 9; ++j) acc += Hinv[(size_t)81 * c + 9 * i + j] * v[(size_t)9 * c + j];
+          out[(size_t)9 * c + i] = acc;
+        }
+    };
+    auto norm = [&](const std::vector<S>& v) { S sq = 0; for (S e : v) sq += e * e; return std::sqrt(sq); };
+    std::vector<S> nb(N), tmp(N), e(N);
+    for (size_t k = 0; k < N; ++k) nb[k] = -b[k];
+    accum.assign(N, S(0));
+    mul_inv(nb, accum);
+    tmp = accum;
+    last_power_termination = 0; last_power_order = power_order;
+    for (int i = 1; i <= power_order; ++i) {
+      sc_right_mul_e0(lambda, tmp.data(), e.data());
+      mul_inv(e, tmp);
+      for (size_t k = 0; k < N; ++k) accum[k] += tmp[k];
+      if (q_tolerance > 0) {
+        const S zeta = S(i) * norm(tmp) / norm(accum);
+        if (zeta < q_tolerance) { last_power_termination = 1; last_power_order = i; break; }
+      }
+    }
+    if (b_out) *b_out = b;
+  }
+  // LinearizorSC::apply / LinearizorPowerSC::apply (linearizor_sc.cpp:206-228): SC back-substitution + camera update
+  S sc_linearizor_apply(std::vector<S>& inc) {
+    std::vector<S> lms_new;
+    const S l_diff = sc_back_substitute(scl, sc_lambda, inc.data(), lms_new);
+    if (!std::isfinite(l_diff)) return std::numeric_limits<S>::quiet_NaN();
+    lms = lms_new;
+    for (size_t k = 0; k < inc.size(); ++k) inc[k] *= sc_scaling[k];
+    for (int c = 0; c < nc; ++c) camera_apply_inc(cams.data() + (size_t)10 * c, inc.data() + (size_t)9 * c);
     return l_diff;
   }
 };

@@ -269,6 +269,31 @@ void orc_normalize(int nc, int nl, double* cams, double* lms, double scale) {
     std::memcpy(diag_blocks_out, d.data(), d.size() * sizeof(S));                                         \
     std::memcpy(y_out, y.data(), y.size() * sizeof(S));                                                   \
   }                                                                                                       \
+  void orc_scl_linearize_##SFX(void* hv) { ((Handle<S>*)hv)->P.sc_linearizor_linearize(); }                      \
+  void orc_scl_get_scaling_##SFX(void* hv, S* out) { auto* h = (Handle<S>*)hv; std::memcpy(out, h->P.sc_scaling.data(), h->P.sc_scaling.size() * sizeof(S)); } \
+  void orc_scl_solve_##SFX(void* hv, S lambda, S* inc, S* b_out, S* inv_out, int* it, int* term) {              \
+    auto* h = (Handle<S>*)hv;                                                                                 \
+    std::vector<S> v, b, inv;                                                                                 \
+    h->P.sc_linearizor_solve(lambda, v, &b, &inv);                                                            \
+    std::memcpy(inc, v.data(), v.size() * sizeof(S));                                                         \
+    if (b_out) std::memcpy(b_out, b.data(), b.size() * sizeof(S));                                            \
+    if (inv_out) std::memcpy(inv_out, inv.data(), inv.size() * sizeof(S));                                    \
+    *it = h->P.last_cg_iterations; *term = h->P.last_cg_termination;                                          \
+  }                                                                                                           \
+  void orc_scl_power_solve_##SFX(void* hv, S lambda, int order, S q_tol, S* inc, S* b_out, int* it, int* term) { \
+    auto* h = (Handle<S>*)hv;                                                                                 \
+    std::vector<S> v, b;                                                                                      \
+    h->P.power_sc_linearizor_solve(lambda, order, q_tol, v, &b);                                              \
+    std::memcpy(inc, v.data(), v.size() * sizeof(S));                                                         \
+    if (b_out) std::memcpy(b_out, b.data(), b.size() * sizeof(S));                                            \
+    *it = h->P.last_power_order; *term = h->P.last_power_termination;                                         \
+  }                                                                                                           \
+  void orc_scl_e0_##SFX(void* hv, S lambda, const S* x, S* y) { ((Handle<S>*)hv)->P.sc_right_mul_e0(lambda, x, y); } \
+  void orc_scl_apply_##SFX(void* hv, const S* inc, S* l_diff) {                                               \
+    auto* h = (Handle<S>*)hv;                                                                                 \
+    std::vector<S> v(inc, inc + (size_t)9 * h->P.nc);                                                         \
+    *l_diff = h->P.sc_linearizor_apply(v);                                                                    \
+  }                                                                                                           \
   void orc_sc_back_substitute_##SFX(void* hv, S lambda, const S* pose_inc, S* l_diff, S* lms_out) {       \
     auto* h = (Handle<S>*)hv;                                                                             \
     std::vector<S> l;                                                                                     \

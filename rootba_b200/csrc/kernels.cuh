@@ -1144,6 +1144,85 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2sc  stage 2 of the Schur-complement solvers (solver_type = SCHUR_COMPLEMENT / POWER_SCHUR_COMPLEMENT)
+//   ref: sc/landmark_block.hpp:215-279 (set_landmark_damping, Hll^-1, add_Hb), solver/linearizor_sc.cpp:112-204.
+//   The landmark is eliminated through the NORMAL equations instead of QR: Hll = Jl^T Jl + lambda I (3x3), factorised
+//   Hll = R^T R (Cholesky, R upper).  Everything downstream is then the SAME data as the QR path with the implicit
+//   operator, because Hll^-1 = R^-1 R^-T:
+//       q1d_i := R^-T Jl_i^T Jp_i   (3x9)        =>  sum_i q1d_i^T (sum_j q1d_j x_j) = Jp^T Jl Hll^-1 Jl^T Jp x  (E_0 x)
+//       rr    := R^-T Jl^T r                      =>  b_i = Jp_i^T r_i - q1d_i^T rr = Jp_i^T (r_i - Jl_i Hll^-1 Jl^T r)
+//       landmark increment = -R^-1 (rr + sum_i q1d_i dp_i) = -Hll^-1 Jl^T (r + Jp dp)
+//   so the reduced operator (k_matvec_implicit*), the SCHUR_JACOBI blocks (k_precond_partial<1>), PCG and the
+//   back-substitution kernel are shared with the square-root solver; only this kernel differs -- and with it the
+//   numerics: the condition number of the landmark block is squared, which is what the QR solver avoids.
+//   One warp per tile, G lanes per landmark, lane per observation.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(128) k_sc_stage2(DevPtrs<S> D, S lambda, int* bad_flag) {
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+    const TileInfo T = D.tiles[t];
+    const int n = T.n, G = T.G;
+    const int g = lane / G, j = lane - g * G;
+    const bool active = g < T.nvalid;
+    const size_t slot0 = (size_t)(T.slot_base + g * n);
+    S h[6] = {0, 0, 0, 0, 0, 0}, gv[3] = {0, 0, 0};
+    if (active) {
+      for (int i = j; i < n; i += G) {
+        const S* jl = D.jl + 6 * (slot0 + i);
+        const S r0 = D.res[2 * (slot0 + i)], r1 = D.res[2 * (slot0 + i) + 1];
+        const S a0 = jl[0], a1 = jl[1], a2 = jl[2], b0 = jl[3], b1 = jl[4], b2 = jl[5];
+        h[0] += a0 * a0 + b0 * b0; h[1] += a0 * a1 + b0 * b1; h[2] += a0 * a2 + b0 * b2;
+        h[3] += a1 * a1 + b1 * b1; h[4] += a1 * a2 + b1 * b2; h[5] += a2 * a2 + b2 * b2;
+        gv[0] += a0 * r0 + b0 * r1; gv[1] += a1 * r0 + b1 * r1; gv[2] += a2 * r0 + b2 * r1;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) h[k] = group_sum(h[k], G);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gv[k] = group_sum(gv[k], G);
+    h[0] += lambda; h[3] += lambda; h[5] += lambda;  // landmark damping: Hll = Jl^T Jl + lambda I (sc/landmark_block.hpp:244-247)
+    // Cholesky Hll = R^T R
+    const S r00 = sqrt(h[0]);
+    const S r01 = h[1] / r00, r02 = h[2] / r00;
+    const S r11 = sqrt(h[3] - r01 * r01);
+    const S r12 = (h[4] - r01 * r02) / r11;
+    const S r22 = sqrt(h[5] - r02 * r02 - r12 * r12);
+    const S rr0 = gv[0] / r00;
+    const S rr1 = (gv[1] - r01 * rr0) / r11;
+    const S rr2 = (gv[2] - r02 * rr0 - r12 * rr1) / r22;
+    if (active && j == 0) {
+      if (!(finite_s(rr0) && finite_s(rr1) && finite_s(rr2) && r22 > S(0))) atomicOr(bad_flag, 1);
+      S* lk = D.lmk + 24 * (size_t)(T.lm_base + g);
+      lk[9] = r00; lk[10] = r01; lk[11] = r02; lk[12] = r11; lk[13] = r12; lk[14] = r22;
+      lk[15] = rr0; lk[16] = rr1; lk[17] = rr2;
+    }
+    if (active) {
+      for (int i = j; i < n; i += G) {
+        const size_t sl = slot0 + i;
+        S jp[20], q[28];
+        load_rec<S, 20>(D.jp + 20 * sl, jp);
+        const S* jl = D.jl + 6 * sl;
+        const S a0 = jl[0], a1 = jl[1], a2 = jl[2], b0 = jl[3], b1 = jl[4], b2 = jl[5];
+        const S r0 = D.res[2 * sl], r1 = D.res[2 * sl + 1];
+        S* go = D.yobs + 9 * sl;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+          const S t0 = a0 * jp[p] + b0 * jp[9 + p], t1 = a1 * jp[p] + b1 * jp[9 + p], t2 = a2 * jp[p] + b2 * jp[9 + p];
+          const S c0 = t0 / r00;
+          const S c1 = (t1 - r01 * c0) / r11;
+          const S c2 = (t2 - r02 * c0 - r12 * c1) / r22;
+          q[p] = c0; q[9 + p] = c1; q[18 + p] = c2;
+          go[p] = jp[p] * r0 + jp[9 + p] * r1 - (c0 * rr0 + c1 * rr1 + c2 * rr2);
+        }
+        q[27] = 0;
+        store_rec<S, 28>(D.q1d + 28 * sl, q);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4i  the same operator in implicit form (opt-in: rba_solver_opts.operator_form = 1; SURVEY 8d last remark)
 //   [Q1d; P] is an orthogonal transform of [Jp; 0], so  P^T P = Jp^T Jp - Q1d^T Q1d  (the identity k_stage2 and
 //   k_precond_partial already use) and, per landmark with observations i,
@@ -1157,7 +1236,8 @@ __global__ void __launch_bounds__(128) k_stage2(DevPtrs<S> D, S lambda, Scratch<
 //   k_cam_reduce_final over the observation CSR.
 // ------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(128) k_matvec_implicit(DevPtrs<S> D, int tile_begin, const S* __restrict__ xvec, const int* done, int pdl) {
+__global__ void __launch_bounds__(128) k_matvec_implicit(DevPtrs<S> D, int tile_begin, const S* __restrict__ xvec, const int* done, int pdl,
+                                                          int e0_only = 0) {
   if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (done && *done) return;
@@ -1199,7 +1279,11 @@ __global__ void __launch_bounds__(128) k_matvec_implicit(DevPtrs<S> D, int tile_
         }
         S* yo = D.yobs + 9 * sl;
 #pragma unroll
-        for (int p = 0; p < 9; ++p) yo[p] = (jp[p] * t0 + jp[9 + p] * t1) - (q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2);
+        // e0_only (Power-SC): y_i = Q1d_i^T u = (Jp^T Jl Hll^-1 Jl^T Jp x)_i alone (sc/linearization_power_sc.hpp:261-287)
+        for (int p = 0; p < 9; ++p) {
+          const S e0 = q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2;
+          yo[p] = e0_only ? e0 : (jp[p] * t0 + jp[9 + p] * t1) - e0;
+        }
       }
     }
   }
@@ -1821,7 +1905,7 @@ __device__ __forceinline__ void lds_rec20(const S* src, S (&v)[20]) {
 // MAXSLOTS <= 64: a lane owns at most two observations (A: i = j, B: i = j + G).
 template <class S, int WARPS, int MAXSLOTS, int NS>
 __global__ void __launch_bounds__(WARPS * 32) k_matvec_implicit_tma(DevPtrs<S> D, int tile_end, const S* __restrict__ xvec,
-                                                                     const int* done, int pdl) {
+                                                                     const int* done, int pdl, int e0_only = 0) {
   static_assert(MAXSLOTS <= 64, "two observations per lane");
   extern __shared__ __align__(128) unsigned char smem_imp[];
   __shared__ __align__(8) uint64_t bars_all[WARPS][NS];
@@ -1926,7 +2010,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_matvec_implicit_tma(DevPtrs<S> D
 #pragma unroll
         for (int p = 0; p < 9; ++p) { t0 += jp[p] * xa[p]; t1 += jp[9 + p] * xa[p]; }
 #pragma unroll
-        for (int p = 0; p < 9; ++p) ya[p] = (jp[p] * t0 + jp[9 + p] * t1) - (q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2);
+        for (int p = 0; p < 9; ++p) {
+          const S e0 = q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2;
+          ya[p] = e0_only ? e0 : (jp[p] * t0 + jp[9 + p] * t1) - e0;
+        }
       }
       if (hasB) {
         lds_rec28<S>(sq + 28 * eB, q);
@@ -1935,7 +2022,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_matvec_implicit_tma(DevPtrs<S> D
 #pragma unroll
         for (int p = 0; p < 9; ++p) { t0 += jp[p] * xb[p]; t1 += jp[9 + p] * xb[p]; }
 #pragma unroll
-        for (int p = 0; p < 9; ++p) yb[p] = (jp[p] * t0 + jp[9 + p] * t1) - (q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2);
+        for (int p = 0; p < 9; ++p) {
+          const S e0 = q[p] * u0 + q[9 + p] * u1 + q[18 + p] * u2;
+          yb[p] = e0_only ? e0 : (jp[p] * t0 + jp[9 + p] * t1) - e0;
+        }
       }
     }
     __syncwarp();
@@ -2339,6 +2429,63 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
     st->iter = i;
     if (mode == 3) { st->norm_b = norm_b; st->term = 0; st->reason = 0; }
     if (done) { st->done = 1; st->term = term; st->reason = reason; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Power-series solve of the reduced camera system (solver_type = POWER_SCHUR_COMPLEMENT, "PoBA"):
+//   ref: sc/linearization_power_sc.hpp:130-160:  accum = Hpp^-1 (-b); tmp = accum;
+//        for i = 1..power_order: tmp = Hpp^-1 (E_0 tmp); accum += tmp; stop when i |tmp| / |accum| < eta.
+//   One 16-CTA cluster like k_pcg_vec: i == 0 initialises, i >= 1 consumes y = E_0 p (camera-reduced by the previous
+//   kernel).  D.p = tmp, D.x = accum, D.inv = Hpp^-1 (block-diagonal, damped), D.inc = the result (already the increment:
+//   H inc = -b).  Norms are accumulated in double.
+// ------------------------------------------------------------------------------------------------
+template <class S>
+__global__ void __launch_bounds__(VEC_THREADS) k_power_vec(DevPtrs<S> D, PcgState* st, int i, double eta, int is_last, int pdl) {
+  __shared__ double cl[4][CL_MAX];
+  const int tid = threadIdx.x;
+  const int cams_per_block = (D.nc + gridDim.x - 1) / gridDim.x;
+  const int cam0 = min(D.nc, (int)blockIdx.x * cams_per_block);
+  const int cam1 = min(D.nc, cam0 + cams_per_block);
+  const int e0 = 9 * cam0, ne = 9 * (cam1 - cam0);
+  if (*reinterpret_cast<const volatile int*>(&st->done)) return;
+  if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (st->done) return;
+  if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  cluster_sync_all();
+  double tt = 0, aa = 0;
+  for (int l = tid; l < ne; l += VEC_THREADS) {
+    const int e = e0 + l;
+    const int cam = e / 9;
+    const S* row = D.inv + 9 * (size_t)e;
+    const S* v = (i == 0 ? D.b : D.y) + 9 * (size_t)cam;
+    S z = 0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) z += row[c] * __ldcg(v + c);
+    if (i == 0) z = -z;
+    const S acc = (i == 0) ? z : D.x[e] + z;
+    D.x[e] = acc;
+    D.p[e] = z;
+    if (is_last || i == 0) D.inc[e] = acc;  // refreshed below on convergence
+    tt += (double)z * (double)z;
+    aa += (double)acc * (double)acc;
+  }
+  { double a2[2] = {tt, aa}; cluster_publish<2>(a2, cl, 0); }
+  cluster_sync_all();
+  const double tn = cluster_total(cl, 0), an = cluster_total(cl, 1);
+  int done = 0, term = 0;
+  double zeta = 0;
+  if (i >= 1) {
+    zeta = (double)i * sqrt(tn) / sqrt(an);
+    if (eta > 0 && zeta < eta) { done = 1; term = 1; }
+  }
+  if (!isfinite(an)) { done = 1; term = 2; }
+  if (done && !is_last && i != 0)
+    for (int l = tid; l < ne; l += VEC_THREADS) D.inc[e0 + l] = D.x[e0 + l];
+  if (blockIdx.x == 0 && tid == 0) {
+    st->iter = i; st->last_zeta = zeta;
+    if (done) { st->done = 1; st->term = term; st->reason = term == 1 ? 1 : 3; }
+    else if (is_last) { st->term = 0; st->reason = 0; }
   }
 }
 

@@ -100,6 +100,7 @@ struct Solver : rba_handle {
   // observation and row chunk) or the observation CSR of the implicit form
   const int* op_slots = nullptr; const ReduceItem* op_items = nullptr; const int* op_item_ptr = nullptr; int n_op_items = 0;
   bool implicit_op = false;
+  int e0_only_flag = 0;          // Power-SC: the implicit operator kernels return E_0 x = Q1d^T Q1d x alone
   bool panel_form = true;        // gradient and SCHUR_JACOBI blocks from the Q2 panels (reference form) instead of the identities
   int imp_tile_split = 0;        // tiles [0, split) have <= IMP_MAXSLOTS slots and take the streamed kernel
   size_t imp_smem = 0; int imp_grid = 1;
@@ -209,7 +210,7 @@ struct Solver : rba_handle {
     nl_total = pv->num_landmarks;
     ko.use_valid_projections_only = opt.use_valid_projections_only;
     ko.robust_norm = opt.robust_norm;
-    ko.write_panel = opt.operator_form == 1 ? 0 : 1;
+    ko.write_panel = (opt.operator_form == 1 || opt.solver_type != 0) ? 0 : 1;
     ko.huber = opt.huber_parameter;
     ko.jacobi_eps = opt.jacobi_scaling_epsilon > 0 ? opt.jacobi_scaling_epsilon : (double)ST<S>::eps_sqrt();  // ref: linearizor_base.cpp:72-79
     std::string msg = build_layout(nc, nl_total, pv->lm_obs_offset, pv->obs_cam_idx, opt.rank, opt.nranks, KPMAX, L);
@@ -242,8 +243,13 @@ struct Solver : rba_handle {
       TRY(upload(&d_csr_y_item_ptr, L.csr_y.cam_item_ptr));
       n_y_items = (int)L.csr_y.items.size();
     }
-    implicit_op = opt.operator_form == 1;
+    implicit_op = opt.operator_form == 1 || opt.solver_type != 0;
     if (opt.operator_form != 0 && opt.operator_form != 1) { g_err = "operator_form must be 0 (dense) or 1 (implicit)"; return RBA_ERR_INVALID_ARGUMENT; }
+    if (opt.solver_type < 0 || opt.solver_type > 2) { g_err = "solver_type must be 0 (SQUARE_ROOT), 1 (SCHUR_COMPLEMENT) or 2 (POWER_SCHUR_COMPLEMENT)"; return RBA_ERR_INVALID_ARGUMENT; }
+    if (opt.solver_type == 2 && opt.nranks > 1) { g_err = "POWER_SCHUR_COMPLEMENT runs on one GPU (the power-series vector kernel has no peer exchange yet)"; return RBA_ERR_UNSUPPORTED; }
+    if (opt.power_order <= 0) opt.power_order = 20;  // solver_options.hpp:270
+    // the Schur-complement solvers share the per-observation records and the implicit operator kernels (k_sc_stage2)
+    if (opt.solver_type != 0) implicit_op = true;
     if (opt.stage2_form != 0 && opt.stage2_form != 1) { g_err = "stage2_form must be 0 (Q2 panel, reference) or 1 (orthogonality identity)"; return RBA_ERR_INVALID_ARGUMENT; }
     // gradient / SCHUR_JACOBI blocks from the stored Q2 panels like the reference, unless there are no panels (implicit operator)
     panel_form = !implicit_op && opt.stage2_form == 0;
@@ -264,7 +270,7 @@ struct Solver : rba_handle {
     D.slot_cam = d_slot_cam; D.slot_lm = d_slot_lm; D.slot_xy = d_xy; D.nslots = L.nslots; D.nc = nc;
     TRY(dalloc(&D.cams, (size_t)10 * nc)); TRY(dalloc(&cams_bk, (size_t)10 * nc));
     TRY(dalloc(&D.lms, (size_t)3 * L.nl_local)); TRY(dalloc(&lms_bk, (size_t)3 * L.nl_local));
-    if (opt.operator_form != 1) TRY(dalloc(&D.panel, (size_t)L.panel_scalars));  // the implicit operator never touches the panels
+    if (ko.write_panel) TRY(dalloc(&D.panel, (size_t)L.panel_scalars));  // the implicit operator never touches the panels
     TRY(dalloc(&D.jp, (size_t)20 * L.nslots));
     TRY(dalloc(&D.q1u, (size_t)28 * L.nslots));
     TRY(dalloc(&D.q1d, (size_t)28 * L.nslots));
@@ -337,6 +343,7 @@ struct Solver : rba_handle {
     {
       // the PCG vector step runs on one thread-block cluster (16 CTAs if the device grants it, else 8)
       CU(cudaFuncSetAttribute(k_pcg_vec<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      CU(cudaFuncSetAttribute(k_power_vec<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       pcg_cluster = 16;
       if (const char* e = getenv("RBA_PDL")) use_pdl = atoi(e) != 0;
       if (const char* e = getenv("RBA_PCG_CLUSTER")) pcg_cluster = std::max(1, std::min(atoi(e), 16));
@@ -587,8 +594,8 @@ struct Solver : rba_handle {
     else  // ref: ipp:149-163 selects perform_qr_givens
       k_linearize_qr<S, true><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags);
     launches += 2;
-    if (opt.preconditioner_type == 0) {
-      // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)
+    if (opt.preconditioner_type == 0 || opt.solver_type == 2) {
+      // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (Power-SC: these blocks are Hpp, sc/linearization_power_sc.hpp:92-128) (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)
       rc = precond_blocks(0, D.jblocks, nullptr, true); if (rc) return rc;
     }
     if (panel_form) {
@@ -649,10 +656,10 @@ struct Solver : rba_handle {
       const int ntl = (int)L.tiles.size();
       const bool p = pdl && use_pdl && imp_tile_split == ntl;  // a single kernel between the PCG vector step and the reduction
       if (imp_tile_split > 0 && use_tma)
-        launch_ex((k_matvec_implicit_tma<S, IMP_WARPS, IMP_MAXSLOTS, IMP_NS>), imp_grid, IMP_WARPS * 32, imp_smem, p, 1, D, imp_tile_split, xvec, done, (int)p);
+        launch_ex((k_matvec_implicit_tma<S, IMP_WARPS, IMP_MAXSLOTS, IMP_NS>), imp_grid, IMP_WARPS * 32, imp_smem, p, 1, D, imp_tile_split, xvec, done, (int)p, e0_only_flag);
       const int tb = use_tma ? imp_tile_split : 0;
       if (tb < ntl)
-        launch_ex(k_matvec_implicit<S>, (ntl - tb + TILE_WARPS - 1) / TILE_WARPS, TILE_WARPS * 32, 0, false, 1, D, tb, xvec, done, 0);
+        launch_ex(k_matvec_implicit<S>, (ntl - tb + TILE_WARPS - 1) / TILE_WARPS, TILE_WARPS * 32, 0, false, 1, D, tb, xvec, done, 0, e0_only_flag);
       ++tm.matvec_launches;
       return;
     }
@@ -713,6 +720,47 @@ struct Solver : rba_handle {
   }
 
   // ref: solver/linearizor_qr.cpp:140-265
+  // Power-series solve of the reduced camera system (ref: sc/linearization_power_sc.hpp:130-160, driven by
+  // solver/linearizor_power_sc.cpp:140-160 with q_tolerance = eta): per term one E_0 application (the implicit operator
+  // kernels with e0_only), the per-camera reduction and k_power_vec; the device convergence flag is polled like in PCG.
+  int power_enqueue(void* inc_out) {
+    int rc = start(ev_pcg); if (rc) return rc;
+    CU(cudaMemsetAsync(d_state, 0, sizeof(PcgState), stream));
+    const int order = opt.power_order, chk = opt.pcg_check_period;
+    rc = launch_ex(k_power_vec<S>, pcg_cluster, VEC_THREADS, 0, false, pcg_cluster, D, d_state, 0, (double)opt.eta, 0, 0); if (rc) return rc;
+    e0_only_flag = 1;
+    int i = 1, pending[2] = {0, 0}, slot = 0;
+    bool finished = false;
+    while (i <= order && !finished) {
+      const int chunk_end = std::min(i + chk - 1, order);
+      for (; i <= chunk_end; ++i) {
+        matvec_kernels(D.p, &d_state->done, true);
+        rc = launch_ex((k_cam_reduce_final<S, false>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items,
+                       n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, 0, nc);
+        if (rc) { e0_only_flag = 0; return rc; }
+        rc = launch_ex(k_power_vec<S>, pcg_cluster, VEC_THREADS, 0, use_pdl, pcg_cluster, D, d_state, i, (double)opt.eta, (int)(i == order), (int)use_pdl);
+        if (rc) { e0_only_flag = 0; return rc; }
+      }
+      CU(cudaMemcpyAsync(&h_state[slot], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+      CU(cudaEventRecord(poll_ev[slot], stream));
+      pending[slot] = 1;
+      const int other = slot ^ 1;
+      if (pending[other]) {
+        CU(cudaEventSynchronize(poll_ev[other]));
+        pending[other] = 0;
+        if (h_state[other].done) finished = true;
+      }
+      slot = other;
+    }
+    e0_only_flag = 0;
+    CU(cudaMemcpyAsync(&h_state[0], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+    if (inc_out) CU(cudaMemcpyAsync(inc_out, D.inc, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
+    rc = stop(ev_pcg); if (rc) return rc;
+    have_inc = true;
+    new_linearization_point = false;
+    return RBA_OK;
+  }
+
   long long solve_l0 = 0;
   int solve_enqueue(double lambda_d, void* inc_out) {
     if (!linearized) { g_err = "rba_solve called before a successful rba_linearize"; return RBA_ERR_STATE; }
@@ -721,11 +769,16 @@ struct Solver : rba_handle {
     tm.matvec_launches = 0;
     int rc = start(ev_stage2); if (rc) return rc;
     // stage 2: landmark damping + gradient (+ SCHUR_JACOBI blocks)
-    if (panel_form) k_stage2<S, true><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc, ko.write_panel);
+    if (opt.solver_type != 0) {
+      // Schur-complement solvers: landmark eliminated through the normal equations (Cholesky of Jl^T Jl + lambda I)
+      CU(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), stream));
+      k_sc_stage2<S><<<tile_grid(sm_count * 8), TILE_WARPS * 32, 0, stream>>>(D, lambda, d_flags);
+    } else if (panel_form) k_stage2<S, true><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc, ko.write_panel);
     else k_stage2<S, false><<<tile_grid(k2_max_blocks), TILE_WARPS * 32, k2_smem, stream>>>(D, lambda, k2_sc, ko.write_panel);
     ++launches;
     rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b, nullptr, panel_form ? D.b0 : nullptr); if (rc) return rc;
-    const bool schur = opt.preconditioner_type == 1;
+    const bool power = opt.solver_type == 2;
+    const bool schur = opt.preconditioner_type == 1 && !power;  // Power-SC inverts Hpp = sum Jp^T Jp + lambda I instead
     if (schur) { rc = panel_form ? precond_blocks(2, D.blocks, D.blocks0, true) : precond_blocks(1, D.blocks, nullptr, true); if (rc) return rc; }
     rc = stop(ev_stage2); if (rc) return rc;
     rc = start(ev_precond); if (rc) return rc;
@@ -735,6 +788,7 @@ struct Solver : rba_handle {
     rc = stop(ev_precond); if (rc) return rc;
     last_lambda = lambda;
     damping_valid = true;
+    if (power) return power_enqueue(inc_out);
     // PCG (ref: cg/conjugate_gradient.hpp:113-298 ; linearizor_base.cpp:81-103)
     rc = start(ev_pcg); if (rc) return rc;
     CU(cudaMemsetAsync(d_state, 0, sizeof(PcgState), stream));
@@ -1012,6 +1066,7 @@ void rba_default_solver_opts(rba_solver_opts* o) {
   o->nranks = 1;
   o->pcg_check_period = 4;
   o->use_cuda_graphs = 0;
+  o->power_order = 20;
 }
 
 int32_t rba_create_f32(const rba_problem_view* p, const rba_solver_opts* o, rba_handle** out) { return rba::create_impl<float>(p, o, out); }

@@ -32,7 +32,8 @@ class ResidualOptions:  # bal/bal_residual_options.hpp:44-63
 
 @dataclasses.dataclass
 class SolverOptions:  # bal/solver_options.hpp (QR-relevant subset, reference defaults)
-    solver_type: str = "SQUARE_ROOT"
+    solver_type: str = "SQUARE_ROOT"              # SQUARE_ROOT | SCHUR_COMPLEMENT | POWER_SCHUR_COMPLEMENT (solver_options.hpp:63-76)
+    power_order: int = 20                         # :270
     optimized_cost: str = "ERROR"                 # ERROR | ERROR_VALID | ERROR_VALID_AVG
     max_num_iterations: int = 20
     min_relative_decrease: float = 0.0           # solver_options.hpp:146-148
@@ -142,8 +143,8 @@ class LinearizorQR:
     { solve(lambda) -> [bal_problem.backup()] -> apply -> compute_error -> (restore on reject) }+ ."""
 
     def __init__(self, bal_problem: BalProblem, options: SolverOptions, summary: dict | None = None):
-        if options.solver_type != "SQUARE_ROOT":
-            raise ValueError("only solver_type=SQUARE_ROOT is provided by rootba_b200")
+        if options.solver_type not in ("SQUARE_ROOT", "SCHUR_COMPLEMENT", "POWER_SCHUR_COMPLEMENT"):
+            raise ValueError(f"solver_type {options.solver_type} is not provided by rootba_b200")
         self.bal_problem = bal_problem
         self.options = options
         self.summary = summary
@@ -167,6 +168,8 @@ class LinearizorQR:
         o.pcg_check_period = options.pcg_check_period
         o.operator_form = {"DENSE": 0, "IMPLICIT": 1}[options.operator_form]
         o.stage2_form = {"PANEL": 0, "IDENTITY": 1}[options.stage2_form]
+        o.solver_type = {"SQUARE_ROOT": 0, "SCHUR_COMPLEMENT": 1, "POWER_SCHUR_COMPLEMENT": 2}[options.solver_type]  # linearizor.cpp:48-65
+        o.power_order = options.power_order
         self._opts = o
         pv = ProblemView(bal_problem.num_cameras(), bal_problem.num_landmarks(), bal_problem.num_observations(),
                          bal_problem.lm_off.ctypes.data, bal_problem.obs_cam.ctypes.data, bal_problem.obs_xy.ctypes.data)
