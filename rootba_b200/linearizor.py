@@ -401,6 +401,27 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
     terminated = False
     it = 0
     max_lm_iter = o.max_num_iterations
+    try:
+        _lm_loop(bal_problem, o, S, linearizor, summary, log_iteration, min_lambda, max_lambda, vee_factor, initial_vee, lam, lambda_vee,
+                 max_lm_iter, verbose)
+    except BaseException:
+        if own:
+            linearizor.close()  # do not leak the device handle when the loop raises (numerical failure during linearisation ...)
+        raise
+    bal_problem.sync_from_device()
+    summary["total_time"] = time.perf_counter() - t_total
+    summary["minimizer_time"] = summary["total_time"] - summary["preprocessor_time"]
+    if own:
+        summary["stats"] = linearizor.stats()
+        linearizor.close()
+    return summary
+
+
+def _lm_loop(bal_problem, o, S, linearizor, summary, log_iteration, min_lambda, max_lambda, vee_factor, initial_vee, lam, lambda_vee,
+             max_lm_iter, verbose):
+    """the body of optimize_lm_ours (solver/bal_bundle_adjustment.cpp:291-521)"""
+    terminated = False
+    it = 0
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         while it <= max_lm_iter and not terminated:
             it_summary = {"iteration": it}
@@ -486,10 +507,3 @@ def bundle_adjust_manual(bal_problem: BalProblem, solver_options: SolverOptions,
                         summary["message"] = "Solver did not converge and reached maximum damping lambda"
     if not terminated:
         summary["message"] = f"Solver did not converge after maximum number of {max_lm_iter} iterations"
-    bal_problem.sync_from_device()
-    summary["total_time"] = time.perf_counter() - t_total
-    summary["minimizer_time"] = summary["total_time"] - summary["preprocessor_time"]
-    if own:
-        summary["stats"] = linearizor.stats()
-        linearizor.close()
-    return summary
