@@ -107,6 +107,8 @@ int main(int argc, char** argv) {
     else if (a == "--residual-huber-parameter") o.huber_parameter = std::stod(next());
     else if (a == "--optimized-cost") { const std::string v = next(); o.optimized_cost = v == "ERROR" ? SolverOptions::OptimizedCost::ERROR : v == "ERROR_VALID" ? SolverOptions::OptimizedCost::ERROR_VALID : SolverOptions::OptimizedCost::ERROR_VALID_AVG; }
     else if (a == "--operator-form") { const std::string v = next(); if (v != "dense" && v != "implicit") { std::cerr << "--operator-form dense|implicit\n"; return 2; } o.operator_form = v == "implicit"; }
+    else if (a == "--solver-type") { const std::string v = next(); o.solver_type = v == "SCHUR_COMPLEMENT" ? SolverOptions::SolverType::SCHUR_COMPLEMENT : v == "POWER_SCHUR_COMPLEMENT" ? SolverOptions::SolverType::POWER_SCHUR_COMPLEMENT : SolverOptions::SolverType::SQUARE_ROOT; }
+    else if (a == "--power-order") o.power_order = std::stoi(next());
     else if (a == "--log-path") log_path = next();
     else if (a == "--loader") { const std::string v = next(); if (v != "parallel" && v != "map") { std::cerr << "--loader parallel|map\n"; return 2; } parallel_loader = v == "parallel"; }
     else if (a == "--num-threads") num_threads = std::stoi(next());
