@@ -1686,6 +1686,7 @@ __device__ __forceinline__ bool stream_produce(PanelStream<S>& ps, const DevPtrs
   if (ps.rows_left == 0) {
     if (ps.next_item >= item_end) return false;
     const MatvecItem it = items[ps.next_item];
+    if (it.nrows == 0) { ps.next_item = item_end; return false; }  // padding of the host's dealing: end of this warp's list
     const TileInfo T = D.tiles[it.tile];
     ps.row_scalars = T.KP * 64;
     ps.src = D.panel + T.panel_off + (size_t)it.row0 * ps.row_scalars;
@@ -1858,6 +1859,7 @@ __global__ void __launch_bounds__(WARPS * 32, RBA_K4_MINB) k_matvec_small_tma(De
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (int q = first; q < item_end; q += stride) {
     const MatvecItem it = items[q];
+    if (it.nrows == 0) break;  // padding: end of this warp's list
     const TileInfo T = D.tiles[it.tile];
     switch (T.KP) {
       case 5: matvec_item_tma<S, 5, NS, STAGE_BYTES>(D, it, T, lane, xvec, ps, consumed, items, item_end, stride, ring, bars); break;
@@ -2060,6 +2062,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_matvec_small(DevPtrs<S> D, const
   S* xs = reinterpret_cast<S*>(smem_raw) + (size_t)wib * scratch_per_warp;
   for (int q = item_begin + blockIdx.x * WARPS + wib; q < item_end; q += gridDim.x * WARPS) {
     const MatvecItem it = items[q];
+    if (it.nrows == 0) continue;  // padding of the host's dealing for the TMA kernel
     const TileInfo T = D.tiles[it.tile];
     switch (T.KP) {
       case 5: matvec_item<S, 5>(D, it, T, lane, xs, xvec); break;

@@ -91,6 +91,8 @@ struct Solver : rba_handle {
   // device-only helpers
   S* cams_bk = nullptr; S* lms_bk = nullptr;
   MatvecItem* d_items = nullptr;
+  std::vector<MatvecItem> dealt_items;  // L.items, the small-KP part dealt to the persistent warps (see init)
+  int n_dealt = 0, dealt_grid = 0;
   long long state_version = 0;     // bumped whenever cameras / landmarks change (set_state, apply, restore)
   rba_residual_info error_cache{}; long long error_cache_version = -1, error_enqueue_version = -1; bool error_cache_valid = false;
   int* d_csr_obs_slots = nullptr; ReduceItem* d_csr_obs_items = nullptr; int* d_csr_obs_item_ptr = nullptr;
@@ -228,7 +230,45 @@ struct Solver : rba_handle {
     TRY(upload(&d_slot_cam, L.slot_cam));
     TRY(upload(&d_slot_lm, L.slot_lm));
     TRY(upload(&d_xy, xy));
-    TRY(upload(&d_items, L.items));
+    // The persistent warps of the TMA matvec take the items q = first + k * (number of warps).  Dealing the items sorted by size
+    // round-robin leaves a warp with up to 1.6x the mean work on Ladybug-1723 (13 045 items for 2 960 warps: some get 5, some
+    // 4, and warp 0 the largest of every round); instead the small-KP items are dealt longest-processing-time-first on the host
+    // (greedy on bytes + a per-item constant) and laid out so that position k * W + w holds the k-th item of warp w, padded
+    // with empty items (nrows = 0 = end of a warp's list).  RBA_MATVEC_DEAL=rr keeps the round-robin order.
+    dealt_items = L.items;
+    n_dealt = (int)L.items.size();
+    {
+      const char* e = getenv("RBA_MATVEC_DEAL");
+      long long deal_ovh = 16;  // ~4 KB per item
+      if (const char* o2 = getenv("RBA_MATVEC_DEAL_OVH")) deal_ovh = atoll(o2);
+      const int nsmall = (int)L.items.size() - L.n_items_large;
+      const int tma_bps = std::max(1, (int)((220 * 1024) / ((size_t)K4_WARPS * K4_NS * K4_STAGE + 1024)));
+      const int W = grid_for(nsmall, K4_WARPS, tma_bps) * K4_WARPS;
+      if (!(e && std::string(e) == "rr") && nsmall > W && !implicit_op) {
+        std::vector<std::vector<int>> lists(W);
+        std::vector<std::pair<long long, int>> heap(W);  // (load, warp), min-heap on the load
+        for (int w = 0; w < W; ++w) heap[w] = {0, w};
+        auto cmp = [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a > b; };
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        for (int q = L.n_items_large; q < (int)L.items.size(); ++q) {  // already sorted by decreasing work
+          std::pop_heap(heap.begin(), heap.end(), cmp);
+          auto& top = heap.back();
+          lists[top.second].push_back(q);
+          top.first += (long long)L.items[q].nrows * L.tiles[L.items[q].tile].KP + deal_ovh;  // rows x KP x 256 B, + a per-item constant
+          std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+        size_t maxlen = 0;
+        for (auto& l : lists) maxlen = std::max(maxlen, l.size());
+        MatvecItem empty{}; empty.tile = 0; empty.row0 = 0; empty.nrows = 0; empty.yslot_base = 0; empty.pad = 0;
+        dealt_items.assign(L.items.begin(), L.items.begin() + L.n_items_large);
+        dealt_items.resize(L.n_items_large + maxlen * W, empty);
+        for (int w = 0; w < W; ++w)
+          for (size_t k = 0; k < lists[w].size(); ++k) dealt_items[L.n_items_large + k * W + w] = L.items[lists[w][k]];
+        n_dealt = (int)dealt_items.size();
+        dealt_grid = W / K4_WARPS;
+      }
+    }
+    TRY(upload(&d_items, dealt_items));
 
     TRY(upload(&d_csr_obs_slots, L.csr_obs.slots));
     TRY(upload(&d_csr_obs_items, L.csr_obs.items));
@@ -663,7 +703,7 @@ struct Solver : rba_handle {
       ++tm.matvec_launches;
       return;
     }
-    const int nitems = (int)L.items.size();
+    const int nitems = n_dealt;
     if (L.n_items_large > 0) {
       k_matvec_large<S, K4_WARPS, KPMAX><<<grid_for(L.n_items_large, K4_WARPS, 4), K4_WARPS * 32, k4_smem_small, stream>>>(
           D, d_items, 0, L.n_items_large, L.k4_scratch_per_warp, xvec, done);
@@ -671,7 +711,7 @@ struct Solver : rba_handle {
     }
     if (nitems > L.n_items_large) {
       if (use_tma) {
-        launch_ex(k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>, grid_for(nitems - L.n_items_large, K4_WARPS, k4_tma_blocks_per_sm), K4_WARPS * 32,
+        launch_ex(k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>, dealt_grid > 0 ? dealt_grid : grid_for(nitems - L.n_items_large, K4_WARPS, k4_tma_blocks_per_sm), K4_WARPS * 32,
                   k4_smem_tma, pdl && use_pdl && L.n_items_large == 0, 1, D, (const MatvecItem*)d_items, L.n_items_large, nitems, L.k4_scratch_per_warp, xvec, done,
                   (int)(pdl && use_pdl && L.n_items_large == 0));
         --launches;
