@@ -620,6 +620,18 @@ __device__ __forceinline__ S* scratch_ptr(const Scratch<S>& sc, S* smem_warp, in
   return sc.gbase + w * sc.gstride;
 }
 
+// Order in which the persistent warps of a tile kernel take their tiles: position k * (number of warps) + w holds the
+// k-th tile of warp w, dealt longest-processing-time-first on the host (a warp's list ends at the first -1).  order ==
+// nullptr: plain round-robin over the tiles.
+struct TileOrder {
+  const int* order;
+  int count;
+};
+__device__ __forceinline__ int tile_at(const TileOrder& to, int idx, int ntiles) {
+  if (!to.order) return idx < ntiles ? idx : -1;
+  return idx < to.count ? __ldg(to.order + idx) : -1;
+}
+
 template <class S>
 struct Rot { S c, s; };
 
@@ -656,13 +668,15 @@ __device__ __forceinline__ void rot_apply(const Rot<S>& g, S& x, S& y) {
 //   the coalesced panel layout.
 // ------------------------------------------------------------------------------------------------
 template <class S, bool GIVENS>
-__global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scratch<S> sc, int* bad_flag) {
+__global__ void __launch_bounds__(128) k_linearize_qr(DevPtrs<S> D, KOpts o, Scratch<S> sc, int* bad_flag, TileOrder to) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using V2 = typename ST<S>::V2;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   S* ws_smem = reinterpret_cast<S*>(smem_raw) + (size_t)wib * sc.smem_cap;
   const S eps = (S)o.jacobi_eps;
-  for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+  for (int idx = blockIdx.x * (blockDim.x >> 5) + wib;; idx += gridDim.x * (blockDim.x >> 5)) {
+    const int t = tile_at(to, idx, D.ntiles);
+    if (t < 0) break;
     const TileInfo T = D.tiles[t];
     const int n = T.n, G = T.G, KP = T.KP;
     const int g = lane / G, j = lane - g * G;
@@ -1371,10 +1385,12 @@ __global__ void k_precond_final(const S* __restrict__ pblk, const int* __restric
 //   lanes' 5 two-scalar loads each (L1 merges the sectors shared by neighbouring observations).
 // ------------------------------------------------------------------------------------------------
 template <class S>
-__global__ void __launch_bounds__(128) k_panel_grad_blocks(DevPtrs<S> D, int want_blocks) {
+__global__ void __launch_bounds__(128) k_panel_grad_blocks(DevPtrs<S> D, int want_blocks, TileOrder to) {
   using V2 = typename ST<S>::V2;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = blockIdx.x * (blockDim.x >> 5) + wib; t < D.ntiles; t += gridDim.x * (blockDim.x >> 5)) {
+  for (int idx = blockIdx.x * (blockDim.x >> 5) + wib;; idx += gridDim.x * (blockDim.x >> 5)) {
+    const int t = tile_at(to, idx, D.ntiles);
+    if (t < 0) break;
     const TileInfo T = D.tiles[t];
     const int n = T.n, G = T.G, KP = T.KP;
     const int lg = 31 - __clz(G);

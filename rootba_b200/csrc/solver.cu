@@ -239,7 +239,7 @@ struct Solver : rba_handle {
     n_dealt = (int)L.items.size();
     {
       const char* e = getenv("RBA_MATVEC_DEAL");
-      long long deal_ovh = 16;  // ~4 KB per item
+      long long deal_ovh = 48;  // per-item constant (~12 KB-equivalent); 0 / 16 / 48 / 128 measured within 1 % of each other
       if (const char* o2 = getenv("RBA_MATVEC_DEAL_OVH")) deal_ovh = atoll(o2);
       const int nsmall = (int)L.items.size() - L.n_items_large;
       const int tma_bps = std::max(1, (int)((220 * 1024) / ((size_t)K4_WARPS * K4_NS * K4_STAGE + 1024)));
@@ -371,6 +371,11 @@ struct Solver : rba_handle {
       };
       TRY(setup(k1_sc, K1_CAP, need1, k1_smem, k1_bps, k1_max_blocks));
       TRY(setup(k2_sc, K2_CAP, need2, k2_smem, k2_bps, k2_max_blocks));
+      // tiles dealt to the persistent warps longest-first (the kernels' work per tile grows like n^2: panel rows x columns)
+      if (!(getenv("RBA_TILE_DEAL") && std::string(getenv("RBA_TILE_DEAL")) == "rr")) {
+        TRY(deal_tiles(tile_grid(k1_max_blocks) * TILE_WARPS, order_k1));
+        TRY(deal_tiles(tile_grid(sm_count * 8) * TILE_WARPS, order_kp));
+      }
       CU(cudaFuncSetAttribute((k_linearize_qr<S, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
       CU(cudaFuncSetAttribute((k_linearize_qr<S, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem));
       CU(cudaFuncSetAttribute((k_stage2<S, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2_smem));
@@ -554,6 +559,41 @@ struct Solver : rba_handle {
     ++launches;
     return RBA_OK;
   }
+  TileOrder order_k1{nullptr, 0}, order_kp{nullptr, 0};
+  // longest-processing-time-first lists of tiles for nw persistent warps, laid out so that position k * nw + w is the k-th
+  // tile of warp w (-1 = end of the warp's list)
+  int deal_tiles(int nw, TileOrder& out) {
+    const int nt = (int)L.tiles.size();
+    if (nt <= nw) return RBA_OK;  // at most one tile per warp: nothing to balance
+    std::vector<int> idx(nt);
+    std::vector<long long> cost(nt);
+    for (int t = 0; t < nt; ++t) {
+      idx[t] = t;
+      const TileInfo& T = L.tiles[t];
+      cost[t] = (long long)2 * T.n * T.KP + (long long)(32 / T.G) * T.n / 2 + 8;  // panel rows x column steps + per-observation work + constant
+    }
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<std::vector<int>> lists(nw);
+    std::vector<std::pair<long long, int>> heap(nw);
+    for (int w = 0; w < nw; ++w) heap[w] = {0, w};
+    auto cmp = [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a > b; };
+    std::make_heap(heap.begin(), heap.end(), cmp);
+    for (int t : idx) {
+      std::pop_heap(heap.begin(), heap.end(), cmp);
+      heap.back().first += cost[t];
+      lists[heap.back().second].push_back(t);
+      std::push_heap(heap.begin(), heap.end(), cmp);
+    }
+    size_t maxlen = 0;
+    for (auto& l : lists) maxlen = std::max(maxlen, l.size());
+    std::vector<int> order(maxlen * nw, -1);
+    for (int w = 0; w < nw; ++w)
+      for (size_t k = 0; k < lists[w].size(); ++k) order[k * nw + w] = lists[w][k];
+    int* d = nullptr;
+    int rc = upload(&d, order); if (rc) return rc;
+    out.order = d; out.count = (int)order.size();
+    return RBA_OK;
+  }
   int tile_grid(int max_blocks) const { return std::max(1, std::min(max_blocks, (D.ntiles + TILE_WARPS - 1) / TILE_WARPS)); }
   int grid_for(long long work_items, int per_block, int blocks_per_sm) const {
     long long g = (work_items + per_block - 1) / per_block;
@@ -630,9 +670,9 @@ struct Solver : rba_handle {
     k_scaling<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.diag2, D.scaling, 9 * nc, (S)ko.jacobi_eps);
     // pass B: linearize (scaled) + Jl scaling + Householder QR + panel write
     if (opt.use_householder_marginalization)
-      k_linearize_qr<S, false><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags);
+      k_linearize_qr<S, false><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags, order_k1);
     else  // ref: ipp:149-163 selects perform_qr_givens
-      k_linearize_qr<S, true><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags);
+      k_linearize_qr<S, true><<<tile_grid(k1_max_blocks), TILE_WARPS * 32, k1_smem, stream>>>(D, ko, k1_sc, d_flags, order_k1);
     launches += 2;
     if (opt.preconditioner_type == 0 || opt.solver_type == 2) {
       // JACOBI: D (sum Jp^T Jp) D from the stored scaled Jacobians (Power-SC: these blocks are Hpp, sc/linearization_power_sc.hpp:92-128) (ref: ipp:554-569, block_sparse_matrix.hpp:89-100)
@@ -643,7 +683,7 @@ struct Solver : rba_handle {
       // SCHUR_JACOBI blocks (ipp:520-552) is accumulated once per linearisation (this shard only; the sum over the
       // shards happens in solve() together with the damping-row part)
       const int want_blocks = opt.preconditioner_type == 1 ? 1 : 0;
-      k_panel_grad_blocks<S><<<tile_grid(sm_count * 8), TILE_WARPS * 32, 0, stream>>>(D, want_blocks);
+      k_panel_grad_blocks<S><<<tile_grid(sm_count * 8), TILE_WARPS * 32, 0, stream>>>(D, want_blocks, order_kp);
       ++launches;
       rc = camera_reduce(d_csr_obs_slots, d_csr_obs_items, n_obs_items, d_csr_obs_item_ptr, D.b0, nullptr, nullptr, false); if (rc) return rc;
       if (want_blocks) { rc = precond_blocks(3, D.blocks0, nullptr, false); if (rc) return rc; }
