@@ -112,7 +112,6 @@ struct Solver : rba_handle {
   double* d_part4 = nullptr;     // [grid][4] partials of the fused PCG step
   int pcg_cluster = 16;
   bool use_pdl = true;
-  int* d_cam_cnt = nullptr;      // per-camera arrival counters of k_cam_reduce_final (zero between launches)
   double* d_epart = nullptr;     // [EBLOCKS][6]
   double* d_red = nullptr;       // [8] reduced doubles (error / l_diff)
   int* d_flags = nullptr;        // [4] bad flags
@@ -329,7 +328,7 @@ struct Solver : rba_handle {
     TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
     TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
     TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
-    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4)); TRY(dalloc(&d_cam_cnt, (size_t)nc));
+    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4));
     pc.nranks = 1; pc.rank = opt.rank;
     if (opt.nranks > 1 && opt.nranks <= MAX_PEERS) {
       pc.off_y = 4096;
@@ -772,13 +771,14 @@ struct Solver : rba_handle {
   int pcg_apply(int i, int mode, int is_last, S lambda) {
     const bool fused = opt.nranks > 1 && peer_ok;
     if (fused) ++ar_seq;
-    // NCCL path: k_cam_reduce_final writes y only for cameras that have observations in this shard; D.y is all-reduced IN
+    // NCCL path: k_cam_reduce_cam writes y only for cameras that have observations in this shard; D.y is all-reduced IN
     // PLACE, so without this the other cameras would carry the previous iteration's global sum into the next all-reduce
     if (opt.nranks > 1 && !fused) CU(cudaMemsetAsync(D.y, 0, (size_t)9 * nc * sizeof(S), stream));
-    int rc = fused ? launch_ex((k_cam_reduce_final<S, true>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
-                               op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, ar_seq, nc)
-                   : launch_ex((k_cam_reduce_final<S, false>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
-                               op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, ar_seq, nc);
+    const int g = std::min(nc, sm_count * 16);
+    int rc = fused ? launch_ex((k_cam_reduce_cam<S, true>), g, 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y,
+                               (const int*)&d_state->done, (int)use_pdl, pc, ar_seq)
+                   : launch_ex((k_cam_reduce_cam<S, false>), g, 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y,
+                               (const int*)&d_state->done, (int)use_pdl, pc, ar_seq);
     if (rc) return rc;
     if (opt.nranks == 1) return pcg_vec(i, mode, true, is_last, lambda);
     if (fused) return pcg_vec(i, mode, true, is_last, lambda, true);
@@ -815,8 +815,8 @@ struct Solver : rba_handle {
       const int chunk_end = std::min(i + chk - 1, order);
       for (; i <= chunk_end; ++i) {
         matvec_kernels(D.p, &d_state->done, true);
-        rc = launch_ex((k_cam_reduce_final<S, false>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items,
-                       n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, 0, nc);
+        rc = launch_ex((k_cam_reduce_cam<S, false>), std::min(nc, sm_count * 16), 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items,
+                       op_item_ptr, nc, D.y, (const int*)&d_state->done, (int)use_pdl, pc, 0);
         if (rc) { e0_only_flag = 0; return rc; }
         rc = launch_ex(k_power_vec<S>, pcg_cluster, VEC_THREADS, 0, use_pdl, pcg_cluster, D, d_state, i, (double)opt.eta, (int)(i == order), (int)use_pdl);
         if (rc) { e0_only_flag = 0; return rc; }
