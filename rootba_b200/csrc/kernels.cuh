@@ -198,21 +198,6 @@ __device__ __forceinline__ void block_sum_store(double (&v)[K], double* out) {
   __syncthreads();
 }
 
-// block-wide sum of one double -> out[blockIdx.x*4 + k] (thread 0)
-__device__ __forceinline__ void block_sum_store4(double v, double* out, int k) {
-  __shared__ double sm4[32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = warp_sum(v);
-  if (lane == 0) sm4[w] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0;
-    for (int q = 0; q < nw; ++q) s += sm4[q];
-    out[blockIdx.x * 4 + k] = s;
-  }
-  __syncthreads();
-}
-
 // sum of n <= 1024 partial doubles in a fixed order, result broadcast to every thread of the block
 __device__ __forceinline__ double block_sum_partials(const double* part, int n, int stride, int off) {
   __shared__ double bs_sm[32];
@@ -2164,7 +2149,7 @@ __global__ void k_cam_final9(const S* __restrict__ partial, const int* __restric
 //   P3  Nash-Sofer test zeta = i (Q_i - Q_{i-1}) / Q_i < eta ; rho, beta ; p = z + beta p   (next iteration's p)
 // ref: cg/conjugate_gradient.hpp:161-295 ; scalars in double, vectors in Scalar, alpha/beta narrowed to Scalar.
 // mode 0 regular iteration, 1 refresh first half (stop after x += alpha p), 2 refresh second half (v = x,
-// r = b - H x), 3 initialisation (x = 0, r = b, z, rho, p = z).  part: [gridDim][4] doubles.
+// r = b - H x), 3 initialisation (x = 0, r = b, z, rho, p = z).
 // y = D.y holds the camera-reduced (and, with several shards, all-reduced) operator output.
 // Cameras are dealt to the CTAs in contiguous ranges; thread t of a CTA owns elements e0 + t + k * blockDim.  Everything
 // that does not depend on the operator output (x, r, p, b and the 9-float row of M^-1) is fetched before the grid
@@ -2223,7 +2208,7 @@ __device__ __forceinline__ S ld_volatile(const S* p) { return *reinterpret_cast<
 
 
 template <class S>
-__global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState* st, double* part, S lambda, int i, int mode,
+__global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState* st, S lambda, int i, int mode,
                                                          double eta, int min_it, int is_last, int pdl, PeerComm pc, int seq) {
   __shared__ S sr[VEC_THREADS * VEC_EPT + 16];
   __shared__ int peer_fail;

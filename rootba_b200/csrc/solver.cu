@@ -107,9 +107,6 @@ struct Solver : rba_handle {
   int imp_tile_split = 0;        // tiles [0, split) have <= IMP_MAXSLOTS slots and take the streamed kernel
   size_t imp_smem = 0; int imp_grid = 1;
   ReduceItem* d_pb_items = nullptr; int* d_pb_item_ptr = nullptr; int n_pb_items = 0;
-  double* d_part = nullptr;      // [NPART][3]
-  double* d_part_pq = nullptr;   // [NPART]
-  double* d_part4 = nullptr;     // [grid][4] partials of the fused PCG step
   int pcg_cluster = 16;
   bool use_pdl = true;
   double* d_epart = nullptr;     // [EBLOCKS][6]
@@ -328,7 +325,7 @@ struct Solver : rba_handle {
     TRY(dalloc(&D.yobs, (size_t)9 * L.nyslots));
     TRY(dalloc(&D.partial, (size_t)9 * std::max(n_obs_items, n_y_items)));
     TRY(dalloc(&D.pblk, (size_t)48 * n_pb_items));
-    TRY(dalloc(&d_part, (size_t)NPART * 3)); TRY(dalloc(&d_part_pq, (size_t)NPART)); TRY(dalloc(&d_part4, (size_t)4096 * 4));
+
     pc.nranks = 1; pc.rank = opt.rank;
     if (opt.nranks > 1 && opt.nranks <= MAX_PEERS) {
       pc.off_y = 4096;
@@ -764,7 +761,7 @@ struct Solver : rba_handle {
   int pcg_vec(int i, int mode, bool pdl, int is_last, S lambda, bool fused_ar = false) {
     PeerComm c = pc;
     if (!fused_ar) c.nranks = 1;
-    return launch_ex(k_pcg_vec<S>, pcg_cluster, VEC_THREADS, 0, pdl && use_pdl, pcg_cluster, D, d_state, d_part4, lambda, i, mode, (double)opt.eta,
+    return launch_ex(k_pcg_vec<S>, pcg_cluster, VEC_THREADS, 0, pdl && use_pdl, pcg_cluster, D, d_state, lambda, i, mode, (double)opt.eta,
                      (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl), c, ar_seq);
   }
   // finish one operator application inside PCG (H v for v = p in mode 0/1, x in mode 2) and do the vector step
