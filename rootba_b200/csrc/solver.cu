@@ -722,9 +722,10 @@ struct Solver : rba_handle {
   }
 
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
+  // one complete operator application outside PCG: y = sum over the landmarks of P^T P x_red (this shard), per camera in D.y
   void matvec_launch(const S* xvec, const int* done) {
     matvec_kernels(xvec, done);
-    k_cam_reduce<S><<<grid_for(n_op_items, 8, 8), 256, 0, stream>>>(D.yobs, op_slots, op_items, n_op_items, D.partial, done);
+    k_cam_reduce_cam<S, false><<<std::min(nc, sm_count * 16), 128, 0, stream>>>((const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y, done, 0, pc, 0);
     ++launches;
   }
   void matvec_kernels(const S* xvec, const int* done, bool pdl = false) {
@@ -784,15 +785,9 @@ struct Solver : rba_handle {
   }
   // q_out = H vec = sum + lambda vec ; optional partial p.q
   int matvec_finish(const S* vec, S* out, S lambda, PcgState* st, double* part) {
-    if (opt.nranks == 1) {
-      k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, D.partial, op_item_ptr, nullptr, vec, out, lambda, part);
-      ++launches;
-    } else {
-      k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, op_item_ptr, nc, D.y, st ? &st->done : nullptr);
-      int rc = allreduce(D.y, (size_t)9 * nc); if (rc) return rc;
-      k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, nullptr, nullptr, D.y, vec, out, lambda, part);
-      launches += 2;
-    }
+    int rc = allreduce(D.y, (size_t)9 * nc); if (rc) return rc;  // no-op on one GPU
+    k_pcg_q<S><<<NPART, 128, 0, stream>>>(D, st, nullptr, nullptr, D.y, vec, out, lambda, part);
+    ++launches;
     return RBA_OK;
   }
 
@@ -1042,6 +1037,7 @@ struct Solver : rba_handle {
   int right_multiply(const void* x, void* y) override {
     if (!linearized || !damping_valid) { g_err = "rba_right_multiply needs rba_linearize + rba_solve first"; return RBA_ERR_STATE; }
     CU(cudaMemcpyAsync(D.z, x, (size_t)9 * nc * sizeof(S), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemsetAsync(D.y, 0, (size_t)9 * nc * sizeof(S), stream));  // cameras without observations in this shard are not written
     matvec_launch(D.z, nullptr);
     int rc = matvec_finish(D.z, D.y, last_lambda, nullptr, nullptr); if (rc) return rc;
     CU(cudaMemcpyAsync(y, D.y, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
