@@ -92,7 +92,7 @@ struct Solver : rba_handle {
   S* cams_bk = nullptr; S* lms_bk = nullptr;
   MatvecItem* d_items = nullptr;
   std::vector<MatvecItem> dealt_items;  // L.items, the small-KP part dealt to the persistent warps (see init)
-  int n_dealt = 0, dealt_grid = 0;
+  int n_dealt = 0, dealt_grid = 0, dealt_bps = 0;
   long long state_version = 0;     // bumped whenever cameras / landmarks change (set_state, apply, restore)
   rba_residual_info error_cache{}; long long error_cache_version = -1, error_enqueue_version = -1; bool error_cache_valid = false;
   int* d_csr_obs_slots = nullptr; ReduceItem* d_csr_obs_items = nullptr; int* d_csr_obs_item_ptr = nullptr;
@@ -238,7 +238,19 @@ struct Solver : rba_handle {
       long long deal_ovh = 48;  // per-item constant (~12 KB-equivalent); 0 / 16 / 48 / 128 measured within 1 % of each other
       if (const char* o2 = getenv("RBA_MATVEC_DEAL_OVH")) deal_ovh = atoll(o2);
       const int nsmall = (int)L.items.size() - L.n_items_large;
-      const int tma_bps = std::max(1, (int)((220 * 1024) / ((size_t)K4_WARPS * K4_NS * K4_STAGE + 1024)));
+      // resident CTAs per SM of the TMA matvec (shared memory: 5; the float64 instance is register-limited to 2): the grid
+      // must be exactly the co-resident CTAs, or the longest-first lists of a later wave would start when the first is done
+      int tma_bps = std::max(1, (int)((220 * 1024) / ((size_t)K4_WARPS * K4_NS * K4_STAGE + 1024)));
+      {
+        const size_t smem = (size_t)K4_WARPS * K4_NS * K4_STAGE;
+        int occ = 0;
+        if (cudaFuncSetAttribute((k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>), K4_WARPS * 32, smem) == cudaSuccess && occ > 0)
+          tma_bps = std::min(tma_bps, occ);
+        else
+          cudaGetLastError();
+      }
+      dealt_bps = tma_bps;
       const int W = grid_for(nsmall, K4_WARPS, tma_bps) * K4_WARPS;
       if (!(e && std::string(e) == "rr") && nsmall > W && !implicit_op) {
         std::vector<std::vector<int>> lists(W);
@@ -408,6 +420,7 @@ struct Solver : rba_handle {
       if (use_tma) {
         CU(cudaFuncSetAttribute((k_matvec_small_tma<S, K4_WARPS, K4_NS, K4_STAGE>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4_smem_tma));
         k4_tma_blocks_per_sm = std::max(1, (int)((220 * 1024) / (k4_smem_tma + 1024)));
+        if (dealt_bps > 0) k4_tma_blocks_per_sm = dealt_bps;
         if (const char* b = getenv("RBA_MATVEC_BLOCKS_PER_SM")) k4_tma_blocks_per_sm = std::max(1, atoi(b));
       }
     }
@@ -724,9 +737,9 @@ struct Solver : rba_handle {
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
   // one complete operator application outside PCG: y = sum over the landmarks of P^T P x_red (this shard), per camera in D.y
   void matvec_launch(const S* xvec, const int* done) {
-    matvec_kernels(xvec, done);
-    k_cam_reduce_cam<S, false><<<std::min(nc, sm_count * 16), 128, 0, stream>>>((const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y, done, 0, pc, 0);
-    ++launches;
+    matvec_kernels(xvec, done, true);  // launched like inside PCG (programmatic dependent launch)
+    launch_ex((k_cam_reduce_cam<S, false>), std::min(nc, sm_count * 16), 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y,
+              done, (int)use_pdl, pc, 0);
   }
   void matvec_kernels(const S* xvec, const int* done, bool pdl = false) {
     if (implicit_op) {
