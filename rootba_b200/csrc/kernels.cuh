@@ -463,52 +463,56 @@ __global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, c
     cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
 }
 
-// Final per-camera reduction of the operator output inside PCG, one block per camera: the segments (ReduceItems) of ONE
-// camera are summed by the four warps of the block -- warp w takes the camera's segments w, w + 4, ... in order, the four
-// per-warp 9-vectors are added in warp order through shared memory -- so the result is complete when the kernel ends,
-// deterministic (fixed association order), and no partial sum travels through global memory (round 1 used per-segment
-// warps + arrival counters + __threadfence; measured 0.4 us slower per PCG iteration).  The camera's sum goes to y, or
-// (several shards, peer exchange) into slot [parity][own rank] of EVERY rank's staging area; cameras without observations
-// in this shard are never written and stay zero there.
+// Same, and the warp that completes the LAST segment of a camera (arrival counter) adds the camera's segment sums in
+// their fixed order and writes y[cam][9]: the result is complete when the kernel ends, deterministic, and needs no
+// second kernel.  cam_cnt must be zero on entry and is left zero.
 template <class S, bool PEERS>
-__global__ void __launch_bounds__(128) k_cam_reduce_cam(const S* __restrict__ src, const int* __restrict__ slots,
-                                                         const ReduceItem* __restrict__ items, const int* __restrict__ cam_item_ptr,
-                                                         int ncams, S* __restrict__ y, const int* done, int pdl, PeerComm pc, int seq) {
-  __shared__ int sidx_all[4][SEG_LEN];
-  __shared__ S part[4][9];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__global__ void __launch_bounds__(256) k_cam_reduce_final(const S* __restrict__ src, const int* __restrict__ slots,
+                                                           const ReduceItem* __restrict__ items, int nitems,
+                                                           const int* __restrict__ cam_item_ptr, S* __restrict__ partial,
+                                                           int* cam_cnt, S* __restrict__ y, const int* done, int pdl,
+                                                           PeerComm pc, int seq, int nc) {
+  __shared__ int sidx_all[8][SEG_LEN];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
   if (done && *reinterpret_cast<const volatile int*>(done)) return;  // monotonic flag, see k_matvec_small_tma
-  // the slot indices are constant: stage this warp's first segment before the grid dependency is awaited
-  int cam = blockIdx.x;
-  int i0 = 0, i1 = 0;
-  if (cam < ncams) { i0 = cam_item_ptr[cam]; i1 = cam_item_ptr[cam + 1]; }
-  if (i0 + w < i1) cam_stage_indices<S>(slots, items[i0 + w], lane, sidx_all[w]);
+  // the slot indices are constant: stage the first item's before the grid dependency is awaited
+  const int it0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  if (it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (done && *done) return;
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  for (; cam < ncams; cam += gridDim.x) {
-    if (cam != (int)blockIdx.x) { i0 = cam_item_ptr[cam]; i1 = cam_item_ptr[cam + 1]; }
-    S acc = 0;  // lanes 0..8: this warp's sum of component `lane`
-    for (int it = i0 + w; it < i1; it += 4) {
-      const ReduceItem I = items[it];
-      if (!(cam == (int)blockIdx.x && it == i0 + w)) cam_stage_indices<S>(slots, I, lane, sidx_all[w]);
-      __shared__ S tmp9[4][9];
-      cam_sum_staged(src, I, lane, tmp9[w], sidx_all[w]);
-      __syncwarp();
-      if (lane < 9) acc += tmp9[w][lane];
-      __syncwarp();
-    }
-    if (lane < 9) part[w][lane] = acc;
-    __syncthreads();
-    if (w == 0 && lane < 9 && i1 > i0) {
-      const S v = ((part[0][lane] + part[1][lane]) + part[2][lane]) + part[3][lane];
+  for (int it = it0; it < nitems; it += gridDim.x * wpb) {
+    const ReduceItem I = items[it];
+    if (it != it0) cam_stage_indices<S>(slots, I, lane, sidx_all[threadIdx.x >> 5]);
+    cam_sum_staged(src, I, lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+    const int i0 = cam_item_ptr[I.cam], i1 = cam_item_ptr[I.cam + 1];
+    // the camera's sum goes to y, or (several shards, peer exchange) into slot [parity][own rank] of EVERY rank's staging
+    // area; cameras without observations in this shard are never written and stay zero there
+    auto emit = [&](S v) {
       if constexpr (PEERS) {
-        for (int d = 0; d < pc.nranks; ++d) peer_ystage<S>(pc, d, seq & 1, pc.rank, ncams)[9 * (size_t)cam + lane] = v;
+        for (int d = 0; d < pc.nranks; ++d) peer_ystage<S>(pc, d, seq & 1, pc.rank, nc)[9 * (size_t)I.cam + lane] = v;
       } else {
-        y[9 * (size_t)cam + lane] = v;
+        y[9 * (size_t)I.cam + lane] = v;
       }
+    };
+    if (i1 - i0 == 1) {
+      if (lane < 9) emit(partial[9 * (size_t)it + lane]);
+      continue;
     }
-    __syncthreads();
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(cam_cnt + I.cam, 1) == i1 - i0 - 1) ? 1 : 0;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+      __threadfence();
+      if (lane < 9) {
+        S sacc = 0;
+        for (int q = i0; q < i1; ++q) sacc += __ldcg(partial + 9 * (size_t)q + lane);
+        emit(sacc);
+      }
+      if (lane == 0) cam_cnt[I.cam] = 0;
+    }
   }
 }
 
@@ -1228,7 +1232,7 @@ __global__ void __launch_bounds__(128) k_sc_stage2(DevPtrs<S> D, S lambda, int* 
 //   the numerical advantage that is the point of the square-root formulation -- hence opt-in, default stays the
 //   reference's dense Q2 panel product (ref: ipp:400-441).
 //   One warp per tile, one lane per observation (as k_stage2); writes yobs[slot][9], reduced per camera by
-//   k_cam_reduce_cam over the observation CSR.
+//   k_cam_reduce_final over the observation CSR.
 // ------------------------------------------------------------------------------------------------
 template <class S>
 __global__ void __launch_bounds__(128) k_matvec_implicit(DevPtrs<S> D, int tile_begin, const S* __restrict__ xvec, const int* done, int pdl,
@@ -2245,7 +2249,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
   const bool peers = pc.nranks > 1 && mode != 3;
   const int par = seq & 1;
   if (peers) {
-    // The producing kernel (k_cam_reduce_cam) has pushed this rank's partial y into every peer's staging area and has
+    // The producing kernel (k_cam_reduce_final) has pushed this rank's partial y into every peer's staging area and has
     // completed.  CTA 0 publishes the sequence number to every rank and waits for the peers' numbers in LOCAL memory;
     // its verdict reaches the other CTAs through distributed shared memory, so that the whole cluster takes the same path.
     if (cluster_ctarank() == 0) {

@@ -112,6 +112,7 @@ struct Solver : rba_handle {
   double* d_epart = nullptr;     // [EBLOCKS][6]
   double* d_red = nullptr;       // [8] reduced doubles (error / l_diff)
   int* d_flags = nullptr;        // [4] bad flags
+  int* d_cam_cnt = nullptr;      // per-camera arrival counters of k_cam_reduce_final (zero between launches)
   PcgState* d_state = nullptr;
   PcgState* h_state = nullptr;   // pinned [2]
   double* h_red = nullptr;       // pinned [8]
@@ -349,6 +350,7 @@ struct Solver : rba_handle {
       TRY(dalloc(&pc.dead, 1));
     }
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
+    TRY(dalloc(&d_cam_cnt, (size_t)nc));
     TRY(dalloc(&d_state, 1));
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
     CU(cudaMallocHost((void**)&h_red, 24 * sizeof(double)));
@@ -737,9 +739,10 @@ struct Solver : rba_handle {
   // operator part of one matvec: yobs = P^T P x_red for every landmark, then per-camera sums -> D.partial
   // one complete operator application outside PCG: y = sum over the landmarks of P^T P x_red (this shard), per camera in D.y
   void matvec_launch(const S* xvec, const int* done) {
-    matvec_kernels(xvec, done, true);  // launched like inside PCG (programmatic dependent launch)
-    launch_ex((k_cam_reduce_cam<S, false>), std::min(nc, sm_count * 16), 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y,
-              done, (int)use_pdl, pc, 0);
+    matvec_kernels(xvec, done);
+    k_cam_reduce_final<S, false><<<grid_for(n_op_items, 8, 8), 256, 0, stream>>>((const S*)D.yobs, op_slots, op_items, n_op_items, op_item_ptr, D.partial,
+                                                                               d_cam_cnt, D.y, done, 0, pc, 0, nc);
+    ++launches;
   }
   void matvec_kernels(const S* xvec, const int* done, bool pdl = false) {
     if (implicit_op) {
@@ -782,14 +785,13 @@ struct Solver : rba_handle {
   int pcg_apply(int i, int mode, int is_last, S lambda) {
     const bool fused = opt.nranks > 1 && peer_ok;
     if (fused) ++ar_seq;
-    // NCCL path: k_cam_reduce_cam writes y only for cameras that have observations in this shard; D.y is all-reduced IN
+    // NCCL path: k_cam_reduce_final writes y only for cameras that have observations in this shard; D.y is all-reduced IN
     // PLACE, so without this the other cameras would carry the previous iteration's global sum into the next all-reduce
     if (opt.nranks > 1 && !fused) CU(cudaMemsetAsync(D.y, 0, (size_t)9 * nc * sizeof(S), stream));
-    const int g = std::min(nc, sm_count * 16);
-    int rc = fused ? launch_ex((k_cam_reduce_cam<S, true>), g, 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y,
-                               (const int*)&d_state->done, (int)use_pdl, pc, ar_seq)
-                   : launch_ex((k_cam_reduce_cam<S, false>), g, 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, op_item_ptr, nc, D.y,
-                               (const int*)&d_state->done, (int)use_pdl, pc, ar_seq);
+    int rc = fused ? launch_ex((k_cam_reduce_final<S, true>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
+                               op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, ar_seq, nc)
+                   : launch_ex((k_cam_reduce_final<S, false>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots,
+                               op_items, n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, ar_seq, nc);
     if (rc) return rc;
     if (opt.nranks == 1) return pcg_vec(i, mode, true, is_last, lambda);
     if (fused) return pcg_vec(i, mode, true, is_last, lambda, true);
@@ -820,8 +822,8 @@ struct Solver : rba_handle {
       const int chunk_end = std::min(i + chk - 1, order);
       for (; i <= chunk_end; ++i) {
         matvec_kernels(D.p, &d_state->done, true);
-        rc = launch_ex((k_cam_reduce_cam<S, false>), std::min(nc, sm_count * 16), 128, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items,
-                       op_item_ptr, nc, D.y, (const int*)&d_state->done, (int)use_pdl, pc, 0);
+        rc = launch_ex((k_cam_reduce_final<S, false>), grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items,
+                       n_op_items, op_item_ptr, D.partial, d_cam_cnt, D.y, (const int*)&d_state->done, (int)use_pdl, pc, 0, nc);
         if (rc) { e0_only_flag = 0; return rc; }
         rc = launch_ex(k_power_vec<S>, pcg_cluster, VEC_THREADS, 0, use_pdl, pcg_cluster, D, d_state, i, (double)opt.eta, (int)(i == order), (int)use_pdl);
         if (rc) { e0_only_flag = 0; return rc; }
