@@ -249,6 +249,36 @@ typedef struct {
 } rba_lm_step_result;
 int32_t rba_lm_step_f32(rba_handle* h, int32_t linearize_first, float lambda, rba_lm_step_result* out);
 int32_t rba_lm_step_f64(rba_handle* h, int32_t linearize_first, double lambda, rba_lm_step_result* out);
+/* The LM loop itself, natively: optimize_lm_ours (solver/bal_bundle_adjustment.cpp:291-521) on top of rba_lm_step, so that
+ * consecutive iterations are separated by one host synchronisation and a few scalar operations instead of an interpreter.
+ * Starts a NEW solve at the handle's current state (lambda = 1 / initial_trust_region_radius, vee = initial_vee) and runs
+ * until the reference's stopping rule fires -- |cost change| <= function_tolerance * cost after a successful step (:174-201),
+ * lambda > 1 / min_trust_region_radius (:378-379), max_num_iterations (:291) -- or `max_steps` iterations have been done.
+ * Same Scalar arithmetic for lambda / vee / step quality as the reference loop (and as the Python / C++ host mirrors, which
+ * stay the tested restatements).  One rba_lm_iteration is written per iteration. */
+typedef struct {
+  double initial_trust_region_radius, min_trust_region_radius, max_trust_region_radius;  /* solver_options.hpp:119-133 */
+  double min_relative_decrease, initial_vee, vee_factor, function_tolerance;              /* :146-148, :136-143, :113 */
+  int32_t max_num_iterations;                                                              /* :106 */
+  int32_t optimized_cost;                                                                  /* 0 ERROR, 1 ERROR_VALID, 2 ERROR_VALID_AVG (:80-96) */
+} rba_lm_opts;
+typedef struct {
+  double lambda;             /* damping used for this iteration's solve */
+  double cost;               /* optimized cost after the step (NaN when the solve failed) */
+  double l_diff;             /* model cost change */
+  double relative_decrease;  /* step quality */
+  double device_seconds;     /* device time of this iteration's stages (CUDA events) */
+  int32_t cg_iterations;
+  int32_t cg_termination;
+  int32_t accepted;          /* step_is_successful */
+  int32_t terminated;        /* the stopping rule fired after this iteration */
+} rba_lm_iteration;
+void rba_default_lm_opts(rba_lm_opts* o);
+/* phase_totals (may be NULL): sums of the stage timings over the iterations done (same fields as rba_get_timings) */
+int32_t rba_lm_run_f32(rba_handle* h, const rba_lm_opts* o, int32_t max_steps, rba_lm_iteration* log, int32_t* steps_done,
+                       int32_t* terminated, rba_stage_timings* phase_totals);
+int32_t rba_lm_run_f64(rba_handle* h, const rba_lm_opts* o, int32_t max_steps, rba_lm_iteration* log, int32_t* steps_done,
+                       int32_t* terminated, rba_stage_timings* phase_totals);
 /* device timings of the last calls */
 int32_t rba_get_timings(const rba_handle* h, rba_stage_timings* out);
 

@@ -56,6 +56,18 @@ class LmStepResult(C.Structure):
     _fields_ = [("cg", CgSummary), ("l_diff", C.c_double), ("cost", ResidualInfo), ("solve_failed", C.c_int32), ("pad_", C.c_int32)]
 
 
+class LmOpts(C.Structure):
+    _fields_ = [("initial_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("initial_vee", C.c_double), ("vee_factor", C.c_double),
+                ("function_tolerance", C.c_double), ("max_num_iterations", C.c_int32), ("optimized_cost", C.c_int32)]
+
+
+class LmIteration(C.Structure):
+    _fields_ = [("lam", C.c_double), ("cost", C.c_double), ("l_diff", C.c_double), ("relative_decrease", C.c_double),
+                ("device_seconds", C.c_double), ("cg_iterations", C.c_int32), ("cg_termination", C.c_int32),
+                ("accepted", C.c_int32), ("terminated", C.c_int32)]
+
+
 class StageTimings(C.Structure):
     _fields_ = [("stage1_time", C.c_double), ("stage2_time", C.c_double),
                 ("compute_preconditioner_time", C.c_double), ("solve_reduced_system_time", C.c_double),

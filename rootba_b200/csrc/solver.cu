@@ -53,6 +53,7 @@ struct rba_handle {
   virtual int solve(double lambda, void* inc_out, rba_cg_summary* cg) = 0;
   virtual int apply(const void* inc, void* l_diff_out, bool update_cameras) = 0;
   virtual int lm_step(bool linearize_first, double lambda, rba_lm_step_result* out) = 0;
+  virtual int lm_run(const rba_lm_opts* o, int max_steps, rba_lm_iteration* log, int* steps_done, int* terminated, rba_stage_timings* totals) = 0;
   virtual int get_timings(rba_stage_timings* out) const = 0;
   virtual int get_stats(rba_workload_stats* out) const = 0;
   virtual int get_scaling(void* scaling, void* diag2) = 0;
@@ -1013,6 +1014,91 @@ struct Solver : rba_handle {
     return rc;  // RBA_NUMERICAL_FAILURE when l_diff is not finite (as rba_apply)
   }
 
+  // optimize_lm_ours (solver/bal_bundle_adjustment.cpp:291-521) on top of lm_step; see rba_lm_run in the header
+  static double cost_of(const rba_residual_info& r, int optimized_cost) {
+    if (optimized_cost == 0) return r.all_error;
+    if (optimized_cost == 1) return r.valid_error;
+    return r.valid_num_obs > 0 ? r.valid_error / (double)r.valid_num_obs : 0.0;
+  }
+  int lm_run(const rba_lm_opts* o, int max_steps, rba_lm_iteration* log, int* steps_done, int* terminated_out, rba_stage_timings* totals) override {
+    const S min_lambda = (S)(1.0 / o->max_trust_region_radius), max_lambda = (S)(1.0 / o->min_trust_region_radius);
+    const S vee_factor = (S)o->vee_factor, initial_vee = (S)o->initial_vee;
+    S lam = (S)(1.0 / o->initial_trust_region_radius), vee = initial_vee;
+    bool new_outer = true, terminated = false;
+    rba_residual_info ri{};
+    if (totals) std::memset(totals, 0, sizeof(*totals));
+    int it = 0;
+    for (; it < max_steps && !terminated; ++it) {
+      rba_lm_iteration& L2 = log[it];
+      std::memset(&L2, 0, sizeof(L2));
+      L2.lambda = (double)lam;
+      const bool lin_first = new_outer;
+      double dev = 0;
+      if (new_outer) {
+        int rc = compute_error(&ri); if (rc) return rc;   // answered from the cache after an accepted step
+        if (!ri.is_numerically_valid) { g_err = "did not expect numerical failure during linearization"; return RBA_NUMERICAL_FAILURE; }  // :307-308
+        dev += tm.residual_evaluation_time;
+        if (totals) totals->residual_evaluation_time += tm.residual_evaluation_time;
+        new_outer = false;
+      }
+      rba_lm_step_result r;
+      int rc = lm_step(lin_first, (double)lam, &r);
+      if (rc < 0) return rc;
+      if (lin_first && rc == RBA_NUMERICAL_FAILURE && !linearized) return rc;  // the linearisation itself failed (reference: CHECK abort)
+      const double t_step = (lin_first ? tm.stage1_time : 0.0) + tm.stage2_time + tm.compute_preconditioner_time + tm.solve_reduced_system_time +
+                            tm.back_substitution_time + tm.update_cameras_time + tm.residual_evaluation_time;
+      dev += t_step;
+      if (totals) {
+        if (lin_first) totals->stage1_time += tm.stage1_time;
+        totals->stage2_time += tm.stage2_time; totals->compute_preconditioner_time += tm.compute_preconditioner_time;
+        totals->solve_reduced_system_time += tm.solve_reduced_system_time; totals->back_substitution_time += tm.back_substitution_time;
+        totals->update_cameras_time += tm.update_cameras_time; totals->residual_evaluation_time += tm.residual_evaluation_time;
+        totals->matvec_launches += tm.matvec_launches;
+      }
+      L2.device_seconds = dev;
+      L2.cg_iterations = r.cg.num_iterations; L2.cg_termination = r.cg.termination_type;
+      L2.l_diff = r.l_diff;
+      L2.cost = std::numeric_limits<double>::quiet_NaN();
+      bool success = false;
+      if (r.solve_failed) {
+        // non-finite increment (:360-399): not applied by the reference; here undone
+        rc = restore(); if (rc) return rc;
+      } else {
+        const S l_diff = (S)r.l_diff;
+        const bool ok = std::isfinite((double)l_diff) && r.cost.is_numerically_valid;
+        L2.cost = cost_of(r.cost, o->optimized_cost);
+        if (ok) {
+          const S f_diff = (S)(cost_of(ri, o->optimized_cost) - cost_of(r.cost, o->optimized_cost));
+          S ld = l_diff;
+          if (o->optimized_cost == 2) ld = (S)(l_diff / (S)ri.valid_num_obs);  // :436-438
+          const S q = (S)(f_diff / ld);
+          L2.relative_decrease = (double)q;
+          success = ld > S(0) && (double)q > o->min_relative_decrease;     // :443-446
+          if (success) {
+            const double fac = std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * (double)q - 1.0, 3));
+            lam = (S)(lam * (S)fac);                                         // :462-466
+            lam = std::max(min_lambda, lam);
+            vee = initial_vee;
+            new_outer = true;
+            const double prev = cost_of(ri, o->optimized_cost == 0 ? 0 : 1), cur = cost_of(r.cost, o->optimized_cost == 0 ? 0 : 1);
+            terminated = std::fabs(prev - cur) <= o->function_tolerance * cur;  // function_tolerance_reached (:174-201)
+          }
+        }
+        if (!success) { rc = restore(); if (rc) return rc; }
+      }
+      if (!success) {
+        lam = (S)(vee * lam); vee = (S)(vee * vee_factor);                   // :378-379, :499-500
+        if (lam > max_lambda) terminated = true;
+      }
+      L2.accepted = success ? 1 : 0;
+      if (it + 1 >= o->max_num_iterations) terminated = true;
+      L2.terminated = terminated ? 1 : 0;
+    }
+    *steps_done = it;
+    *terminated_out = terminated ? 1 : 0;
+    return RBA_OK;
+  }
+
   int get_timings(rba_stage_timings* out) const override { *out = tm; out->kernel_launches = launches; return RBA_OK; }
   int get_stats(rba_workload_stats* out) const override {
     std::memset(out, 0, sizeof(*out));
@@ -1328,6 +1414,19 @@ int32_t rba_apply_f32(rba_handle* h, const float* inc, float* l) { CHECK_TYPE(h,
 int32_t rba_apply_f64(rba_handle* h, const double* inc, double* l) { CHECK_TYPE(h, 8); return h->apply(inc, l, true); }
 int32_t rba_lm_step_f32(rba_handle* h, int32_t linearize_first, float lambda, rba_lm_step_result* out) { CHECK_TYPE(h, 4); return h->lm_step(linearize_first != 0, lambda, out); }
 int32_t rba_lm_step_f64(rba_handle* h, int32_t linearize_first, double lambda, rba_lm_step_result* out) { CHECK_TYPE(h, 8); return h->lm_step(linearize_first != 0, lambda, out); }
+void rba_default_lm_opts(rba_lm_opts* o) {  /* defaults of SolverOptions (solver_options.hpp) */
+  o->initial_trust_region_radius = 1e4; o->min_trust_region_radius = 1e-32; o->max_trust_region_radius = 1e16;
+  o->min_relative_decrease = 0.0; o->initial_vee = 2.0; o->vee_factor = 2.0; o->function_tolerance = 1e-6;
+  o->max_num_iterations = 20; o->optimized_cost = 0;
+}
+int32_t rba_lm_run_f32(rba_handle* h, const rba_lm_opts* o, int32_t max_steps, rba_lm_iteration* log, int32_t* steps_done, int32_t* terminated, rba_stage_timings* totals) {
+  CHECK_TYPE(h, 4); if (!o || !log || !steps_done || !terminated || max_steps < 0) { rba::g_err = "bad arguments"; return RBA_ERR_INVALID_ARGUMENT; }
+  return h->lm_run(o, max_steps, log, steps_done, terminated, totals);
+}
+int32_t rba_lm_run_f64(rba_handle* h, const rba_lm_opts* o, int32_t max_steps, rba_lm_iteration* log, int32_t* steps_done, int32_t* terminated, rba_stage_timings* totals) {
+  CHECK_TYPE(h, 8); if (!o || !log || !steps_done || !terminated || max_steps < 0) { rba::g_err = "bad arguments"; return RBA_ERR_INVALID_ARGUMENT; }
+  return h->lm_run(o, max_steps, log, steps_done, terminated, totals);
+}
 int32_t rba_back_substitute_f32(rba_handle* h, const float* inc, float* l) { CHECK_TYPE(h, 4); return h->apply(inc, l, false); }
 int32_t rba_back_substitute_f64(rba_handle* h, const double* inc, double* l) { CHECK_TYPE(h, 8); return h->apply(inc, l, false); }
 int32_t rba_get_timings(const rba_handle* h, rba_stage_timings* out) { return h->get_timings(out); }

@@ -20,7 +20,7 @@ import time
 import numpy as np
 
 from . import _lib
-from ._lib import (CgSummary, LmStepResult, ProblemView, RbaError, ResidualInfo, SolverOpts, StageTimings, WorkloadStats,
+from ._lib import (CgSummary, LmIteration, LmOpts, LmStepResult, ProblemView, RbaError, ResidualInfo, SolverOpts, StageTimings, WorkloadStats,
                    check, struct_to_dict)
 
 
@@ -282,6 +282,26 @@ class LinearizorQR:
                 "cost": {"all": {"num_obs": ri.all_num_obs, "error": ri.all_error, "residual_sum": ri.all_residual_sum},
                          "valid": {"num_obs": ri.valid_num_obs, "error": ri.valid_error, "residual_sum": ri.valid_residual_sum},
                          "is_numerically_valid": bool(ri.is_numerically_valid)}}
+
+    def lm_run(self, max_steps: int, options: "SolverOptions | None" = None):
+        """optimize_lm_ours natively (rba_lm_run): a NEW solve from the current device state, until the reference's stopping rule
+        or `max_steps` iterations.  Returns (list of per-iteration dicts, terminated, phase totals in seconds)."""
+        o = options or self.options
+        lo = LmOpts()
+        _lib.lib().rba_default_lm_opts(C.byref(lo))
+        lo.initial_trust_region_radius, lo.min_trust_region_radius = o.initial_trust_region_radius, o.min_trust_region_radius
+        lo.max_trust_region_radius, lo.min_relative_decrease = o.max_trust_region_radius, o.min_relative_decrease
+        lo.initial_vee, lo.vee_factor, lo.function_tolerance = o.initial_vee, o.vee_factor, o.function_tolerance
+        lo.max_num_iterations = o.max_num_iterations
+        lo.optimized_cost = {"ERROR": 0, "ERROR_VALID": 1, "ERROR_VALID_AVG": 2}[o.optimized_cost]
+        log = (LmIteration * max(max_steps, 1))()
+        done, term, tot = C.c_int32(), C.c_int32(), StageTimings()
+        check(getattr(_lib.lib(), f"rba_lm_run_{self.sfx}")(self.h, C.byref(lo), int(max_steps), log, C.byref(done), C.byref(term), C.byref(tot)),
+              allow_numerical_failure=True)
+        its = [{"lambda": log[k].lam, "cost": log[k].cost, "l_diff": log[k].l_diff, "relative_decrease": log[k].relative_decrease,
+                "device_seconds": log[k].device_seconds, "cg_iterations": log[k].cg_iterations, "cg_termination": log[k].cg_termination,
+                "accepted": bool(log[k].accepted), "terminated": bool(log[k].terminated)} for k in range(done.value)]
+        return its, bool(term.value), struct_to_dict(tot)
 
     # ---- LinearizationQR-level access (tests) ----
     def timings(self) -> dict:

@@ -351,6 +351,35 @@ def test_lm_step_fused_equals_separate_calls(small_problem, dtype):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("dtype,kw", [(np.float64, {}), (np.float32, {}), (np.float64, {"optimized_cost": "ERROR_VALID"}),
+                                      (np.float32, {"robust_norm": "HUBER", "huber_parameter": 2.0})])
+def test_native_lm_loop_equals_the_python_loop(small_problem, dtype, kw):
+    """rba_lm_run (optimize_lm_ours inside the library, one host synchronisation per iteration) reproduces the Python mirror
+    of the same loop (bundle_adjust_manual, separate entry points) bit for bit: cost, decisions, PCG iterations, final state"""
+    import rootba_b200 as rb
+    so = rb.SolverOptions(max_num_iterations=8)
+    if "optimized_cost" in kw:
+        so.optimized_cost = kw["optimized_cost"]
+    if "robust_norm" in kw:
+        so.residual.robust_norm, so.residual.huber_parameter = kw["robust_norm"], kw["huber_parameter"]
+    bpa, bpb = rb.BalProblem.from_arrays(small_problem, dtype), rb.BalProblem.from_arrays(small_problem, dtype)
+    summ = rb.bundle_adjust_manual(bpa, so)
+    lin = rb.LinearizorQR.create(bpb, so)
+    its, term, tot = lin.lm_run(64)
+    py = summ["iterations"][1:]
+    assert len(its) == len(py) and term == (summ["termination_type"] == "CONVERGENCE" or len(py) >= so.max_num_iterations)
+    key = "all" if so.optimized_cost == "ERROR" else "valid"
+    for a, b in zip(py, its):
+        assert bool(a["step_is_successful"]) == b["accepted"], a["iteration"]
+        assert a["linear_solver_iterations"] == b["cg_iterations"]
+        assert a["cost"][key]["error"] == b["cost"], (a["iteration"], a["cost"][key]["error"], b["cost"])
+        assert a["lam"] == b["lambda"]
+    lin.download_state()
+    assert np.array_equal(bpa.cams, bpb.cams) and np.array_equal(bpa.lms, bpb.lms)
+    assert tot["solve_reduced_system_time"] > 0 and all(i["device_seconds"] > 0 for i in its)
+    lin.close()
+
+
 @pytest.mark.parametrize("config,dtype,kw", [
     ("ladybug-1723", np.float32, {}),                                      # BASELINE configs[1]
     ("trafalgar-257", np.float64, {"preconditioner_type": "JACOBI"}),      # BASELINE configs[2]
