@@ -454,13 +454,24 @@ __device__ __forceinline__ void cam_reduce_item(const S* __restrict__ src, const
 template <class S>
 __global__ void __launch_bounds__(256) k_cam_reduce(const S* __restrict__ src, const int* __restrict__ slots,
                                                      const ReduceItem* __restrict__ items, int nitems,
-                                                     S* __restrict__ partial, const int* done) {
-  if (done && *done) return;
+                                                     S* __restrict__ partial, const int* done, int pdl) {
+  // `done` is written only by the PCG vector kernel BEFORE the operator kernel this one depends on: it is final here
+  if (done && *reinterpret_cast<const volatile int*>(done)) return;
   __shared__ int sidx_all[8][SEG_LEN];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int it = blockIdx.x * wpb + (threadIdx.x >> 5); it < nitems; it += gridDim.x * wpb)
-    cam_reduce_item(src, slots, items[it], lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+  // the slot indices are constant: stage the first item's before the grid dependency is awaited
+  const int it0 = blockIdx.x * wpb + (threadIdx.x >> 5);
+  if (it0 < nitems) cam_stage_indices<S>(slots, items[it0], lane, sidx_all[threadIdx.x >> 5]);
+  if (pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  for (int it = it0; it < nitems; it += gridDim.x * wpb) {
+    const ReduceItem I = items[it];
+    if (it != it0) cam_stage_indices<S>(slots, I, lane, sidx_all[threadIdx.x >> 5]);
+    cam_sum_staged(src, I, lane, partial + 9 * (size_t)it, sidx_all[threadIdx.x >> 5]);
+  }
 }
 
 // Same, and the warp that completes the LAST segment of a camera (arrival counter) adds the camera's segment sums in
@@ -2213,7 +2224,8 @@ __device__ __forceinline__ S ld_volatile(const S* p) { return *reinterpret_cast<
 
 template <class S>
 __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState* st, S lambda, int i, int mode,
-                                                         double eta, int min_it, int is_last, int pdl, PeerComm pc, int seq) {
+                                                         double eta, int min_it, int is_last, int pdl, PeerComm pc, int seq,
+                                                         const int* __restrict__ cam_item_ptr) {
   __shared__ S sr[VEC_THREADS * VEC_EPT + 16];
   __shared__ int peer_fail;
   __shared__ double cl_go;          // multi-GPU: CTA 0's verdict on the peer exchange (distributed shared memory)
@@ -2241,10 +2253,26 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
       qv[k] = 0; zv[k] = 0;
     }
   }
+  // one GPU: the operator's per-camera sums arrive as per-segment partial sums (k_cam_reduce); the segment range of every
+  // element's camera is constant and fetched here, ahead of the grid dependency
+  int pi0[VEC_EPT], pi1[VEC_EPT];
+#pragma unroll
+  for (int k = 0; k < VEC_EPT; ++k) {
+    const int l = tid + k * VEC_THREADS;
+    const bool on = cached && cam_item_ptr && l < ne;
+    const int cam = (e0 + (on ? l : 0)) / 9;
+    pi0[k] = on ? __ldg(cam_item_ptr + cam) : 0;
+    pi1[k] = on ? __ldg(cam_item_ptr + cam + 1) : 0;
+  }
+  // scalars of the previous vector step: that kernel completed before the operator kernel this launch depends on, so
+  // they (and the `done` flag read above) are final already
+  const double rho_cur = st->rho[cur], q0_cur = st->q0[cur];
+  // every CTA of the cluster runs (and stays) before the first distributed-shared-memory store.  A CTA that left above
+  // does not hold the others up (the barrier waits for non-exited threads only), and in that case every CTA leaves
+  // before it stores anything: the flag is final
+  cluster_sync_all();
   if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (st->done) return;
   if (pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  cluster_sync_all();  // every CTA of the cluster runs (and stays) before the first distributed-shared-memory store
   double alpha = 0;
   const bool peers = pc.nranks > 1 && mode != 3;
   const int par = seq & 1;
@@ -2272,6 +2300,12 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
   const S* ys = peers ? peer_ystage<S>(pc, pc.rank, par, 0, D.nc) : nullptr;
   const size_t ystride = (size_t)9 * D.nc;
   auto load_y = [&](int e) -> S {
+    if (!peers && cam_item_ptr) {  // segment sums in their fixed order, like k_cam_reduce_final's last arriver
+      const int cam = e / 9, c = e - 9 * cam;
+      S sacc = 0;
+      for (int q = __ldg(cam_item_ptr + cam), q1 = __ldg(cam_item_ptr + cam + 1); q < q1; ++q) sacc += __ldcg(D.partial + 9 * (size_t)q + c);
+      return sacc;
+    }
     if (!peers) return __ldcg(D.y + e);
     S sacc = 0;  // rank order: bit-identical on every rank; __ldcg: the slots are written by remote stores, L1 may be stale
 #pragma unroll
@@ -2288,7 +2322,13 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
         const int l = tid + k * VEC_THREADS;
         if (l < ne) {
           const S vv = (mode == 2) ? xv[k] : pv[k];
-          qv[k] = load_y(e0 + l) + lambda * vv;
+          S yk;
+          if (!peers && cam_item_ptr) {
+            const int c = (e0 + l) % 9;
+            yk = 0;
+            for (int q = pi0[k]; q < pi1[k]; ++q) yk += __ldcg(D.partial + 9 * (size_t)q + c);
+          } else yk = load_y(e0 + l);
+          qv[k] = yk + lambda * vv;
           acc += (double)(vv * qv[k]);
         }
       }
@@ -2311,7 +2351,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
     int term = 0, reason = 0;
     if (pq <= 0 || isinf(pq)) { fail = true; term = 0; reason = 5; }
     else {
-      alpha = st->rho[cur] / pq;
+      alpha = rho_cur / pq;
       if (isinf(alpha)) { fail = true; term = 2; reason = 6; }
     }
     if (fail) {  // uniform across the cluster: nobody reaches the next barrier
@@ -2399,13 +2439,13 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
   } else {
     const double xbr_t = cluster_total(cl, 2);
     q1 = -xbr_t;
-    zeta = (double)i * (q1 - st->q0[cur]) / q1;
+    zeta = (double)i * (q1 - q0_cur) / q1;
     if (zeta < eta && i >= min_it) { done = 1; term = 1; reason = 1; }
   }
   if (!done) {
     if (rho_new == 0.0 || isinf(rho_new)) { done = 1; term = 2; reason = 3; }
     else if (mode != 3) {
-      beta = rho_new / st->rho[cur];
+      beta = rho_new / rho_cur;
       if (beta == 0.0 || isinf(beta)) { done = 1; term = 2; reason = 4; }
     }
   }

@@ -110,6 +110,7 @@ struct Solver : rba_handle {
   ReduceItem* d_pb_items = nullptr; int* d_pb_item_ptr = nullptr; int n_pb_items = 0;
   int pcg_cluster = 16;
   bool use_pdl = true;
+  bool pcg_partials = true;      // one GPU: k_pcg_vec consumes the per-segment sums of k_cam_reduce (RBA_PCG_PARTIALS=0: k_cam_reduce_final)
   double* d_epart = nullptr;     // [EBLOCKS][6]
   double* d_red = nullptr;       // [8] reduced doubles (error / l_diff)
   int* d_flags = nullptr;        // [4] bad flags
@@ -402,6 +403,7 @@ struct Solver : rba_handle {
       CU(cudaFuncSetAttribute(k_power_vec<S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       pcg_cluster = 16;
       if (const char* e = getenv("RBA_PDL")) use_pdl = atoi(e) != 0;
+      if (const char* e = getenv("RBA_PCG_PARTIALS")) pcg_partials = atoi(e) != 0;
       if (const char* e = getenv("RBA_PCG_CLUSTER")) pcg_cluster = std::max(1, std::min(atoi(e), 16));
       for (; pcg_cluster > 1; pcg_cluster >>= 1) {
         cudaLaunchConfig_t cfg = {};
@@ -616,7 +618,7 @@ struct Solver : rba_handle {
   // deterministic per-camera sum of yobs[slot][9] over a CSR -> dst[9 nc] (+ all-reduce across shards)
   int camera_reduce(const int* slots, const ReduceItem* items, int nitems, const int* item_ptr, S* dst, const int* done,
                     const S* addend = nullptr, bool reduce_ranks = true) {
-    k_cam_reduce<S><<<grid_for(nitems, 8, 8), 256, 0, stream>>>(D.yobs, slots, items, nitems, D.partial, done);
+    k_cam_reduce<S><<<grid_for(nitems, 8, 8), 256, 0, stream>>>(D.yobs, slots, items, nitems, D.partial, done, 0);
     k_cam_final9<S><<<(9 * nc + 255) / 256, 256, 0, stream>>>(D.partial, item_ptr, nc, dst, done, addend);
     launches += 2;
     return reduce_ranks ? allreduce(dst, (size_t)9 * nc) : RBA_OK;
@@ -776,14 +778,22 @@ struct Solver : rba_handle {
     }
     ++tm.matvec_launches;
   }
-  int pcg_vec(int i, int mode, bool pdl, int is_last, S lambda, bool fused_ar = false) {
+  int pcg_vec(int i, int mode, bool pdl, int is_last, S lambda, bool fused_ar = false, bool from_partials = false) {
     PeerComm c = pc;
     if (!fused_ar) c.nranks = 1;
     return launch_ex(k_pcg_vec<S>, pcg_cluster, VEC_THREADS, 0, pdl && use_pdl, pcg_cluster, D, d_state, lambda, i, mode, (double)opt.eta,
-                     (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl), c, ar_seq);
+                     (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl), c, ar_seq, from_partials ? op_item_ptr : (const int*)nullptr);
   }
   // finish one operator application inside PCG (H v for v = p in mode 0/1, x in mode 2) and do the vector step
   int pcg_apply(int i, int mode, int is_last, S lambda) {
+    if (opt.nranks == 1 && pcg_partials) {
+      // one GPU: the vector kernel adds the per-segment sums itself (same order as k_cam_reduce_final's last arriver:
+      // bit-identical) -- no arrival counters, fences or second pass in the reduction
+      int rc = launch_ex(k_cam_reduce<S>, grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, n_op_items, D.partial,
+                         (const int*)&d_state->done, (int)use_pdl);
+      if (rc) return rc;
+      return pcg_vec(i, mode, true, is_last, lambda, false, true);
+    }
     const bool fused = opt.nranks > 1 && peer_ok;
     if (fused) ++ar_seq;
     // NCCL path: k_cam_reduce_final writes y only for cameras that have observations in this shard; D.y is all-reduced IN
