@@ -74,7 +74,7 @@ typedef struct {
   int32_t device;                          /* CUDA device ordinal, -1 = current */
   int32_t rank;                            /* landmark shard owned by this handle */
   int32_t nranks;                          /* 1 = single GPU */
-  int32_t pcg_check_period;                /* host polls the device convergence flag every this many CG iterations (0 -> 4) */
+  int32_t pcg_check_period;                /* CG iterations the host enqueues ahead of the progress the device publishes (NCCL exchange: poll period) (0 -> 4) */
   int32_t use_cuda_graphs;                 /* reserved, ignored: the kernels of a PCG iteration are chained with programmatic
                                               dependent launch + a device-side convergence flag instead of graph capture */
   int32_t operator_form;                   /* PCG operator (Q2^T Jp)^T (Q2^T Jp) x: 0 = dense Q2 panels, as the reference

@@ -428,15 +428,19 @@ __device__ __forceinline__ void cam_sum_staged(const S* __restrict__ src, const 
   const int s3 = lane / 9, c = lane - 9 * s3;
   const bool on = lane < 27;
   S acc = 0;
-  for (int base = 0; base < cnt; base += 48) {
-    S v[16];
+#ifndef RBA_CAM_DEPTH
+#define RBA_CAM_DEPTH 16  /* value loads in flight per lane; 3 * depth slots per round */
+#endif
+  constexpr int DEPTH = RBA_CAM_DEPTH;
+  for (int base = 0; base < cnt; base += 3 * DEPTH) {
+    S v[DEPTH];
 #pragma unroll
-    for (int t = 0; t < 16; ++t) {
+    for (int t = 0; t < DEPTH; ++t) {
       const int e = base + 3 * t + s3;
       v[t] = (on && e < cnt) ? src[9 * (size_t)sidx[e] + c] : S(0);
     }
 #pragma unroll
-    for (int t = 0; t < 16; ++t) acc += v[t];
+    for (int t = 0; t < DEPTH; ++t) acc += v[t];
   }
   __syncwarp();
   // lanes c, c + 9, c + 18 hold the three partial sums of component c
@@ -2221,11 +2225,22 @@ constexpr int VEC_EPT = 2;
 template <class S>
 __device__ __forceinline__ S ld_volatile(const S* p) { return *reinterpret_cast<const volatile S*>(p); }
 
+// Progress of the PCG loop in host-mapped pinned memory: prog[0] = last completed iteration, prog[1] = 1 once the solve has
+// ended.  The host reads it without any stream operation to decide how far ahead it may enqueue (Solver::solve_enqueue).
+__device__ __forceinline__ void pcg_publish_progress(int* prog, int iter, int done) {
+  if (!prog) return;
+  *reinterpret_cast<volatile int*>(prog) = iter;
+  if (done) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(prog + 1) = 1;
+  }
+}
+
 
 template <class S>
 __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState* st, S lambda, int i, int mode,
                                                          double eta, int min_it, int is_last, int pdl, PeerComm pc, int seq,
-                                                         const int* __restrict__ cam_item_ptr) {
+                                                         const int* __restrict__ cam_item_ptr, int* prog) {
   __shared__ S sr[VEC_THREADS * VEC_EPT + 16];
   __shared__ int peer_fail;
   __shared__ double cl_go;          // multi-GPU: CTA 0's verdict on the peer exchange (distributed shared memory)
@@ -2293,7 +2308,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
     }
     cluster_sync_all();
     if (cl_go < 0) {  // uniform over the cluster: a peer never published (dead rank); the solve is reported as FAILURE
-      if (blockIdx.x == 0 && tid == 0) { st->done = 1; st->term = 2; st->reason = 99; st->iter = i; }
+      if (blockIdx.x == 0 && tid == 0) { st->done = 1; st->term = 2; st->reason = 99; st->iter = i; pcg_publish_progress(prog, i, 1); }
       return;
     }
   }
@@ -2356,7 +2371,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
     }
     if (fail) {  // uniform across the cluster: nobody reaches the next barrier
       for (int l = tid; l < ne; l += VEC_THREADS) D.inc[e0 + l] = -D.x[e0 + l];
-      if (blockIdx.x == 0 && tid == 0) { st->done = 1; st->term = term; st->reason = reason; st->last_pq = pq; st->iter = i; }
+      if (blockIdx.x == 0 && tid == 0) { st->done = 1; st->term = term; st->reason = reason; st->last_pq = pq; st->iter = i; pcg_publish_progress(prog, i, 1); }
       return;
     }
     if (blockIdx.x == 0 && tid == 0) { st->last_pq = pq; st->last_alpha = alpha; }
@@ -2473,6 +2488,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_pcg_vec(DevPtrs<S> D, PcgState*
     st->iter = i;
     if (mode == 3) { st->norm_b = norm_b; st->term = 0; st->reason = 0; }
     if (done) { st->done = 1; st->term = term; st->reason = reason; }
+    pcg_publish_progress(prog, i, done || is_last);
   }
 }
 

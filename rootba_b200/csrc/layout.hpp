@@ -82,7 +82,10 @@ struct Layout {
 
 constexpr int KP_SMALL_MAX = 9;    // classes with G <= 32 and <= 18 columns per lane
 constexpr int ROWS_PER_ITEM = 32;  // row chunk of long tracks
-constexpr int SEG_LEN = 96;        // camera slot-list segment reduced by one warp
+#ifndef RBA_SEG_LEN
+#define RBA_SEG_LEN 96
+#endif
+constexpr int SEG_LEN = RBA_SEG_LEN;  // camera slot-list segment reduced by one warp
 constexpr int PB_SEG_LEN = 16;     // observations per thread in the preconditioner-block kernel
 
 // group size for a track length (see DESIGN.md "track-length classes")

@@ -110,6 +110,8 @@ struct Solver : rba_handle {
   ReduceItem* d_pb_items = nullptr; int* d_pb_item_ptr = nullptr; int n_pb_items = 0;
   int pcg_cluster = 16;
   bool use_pdl = true;
+  int* h_prog = nullptr; int* d_prog = nullptr;  // PCG progress in host-mapped pinned memory: [0] last completed iteration, [1] solve ended
+  int pcg_solve_id = 0;
   bool pcg_partials = true;      // one GPU: k_pcg_vec consumes the per-segment sums of k_cam_reduce (RBA_PCG_PARTIALS=0: k_cam_reduce_final)
   double* d_epart = nullptr;     // [EBLOCKS][6]
   double* d_red = nullptr;       // [8] reduced doubles (error / l_diff)
@@ -146,6 +148,7 @@ struct Solver : rba_handle {
     if (comm && nccl) nccl->CommDestroy(comm);
     for (void* p : ipc_opened) cudaIpcCloseMemHandle(p);
     for (void* p : allocs) cudaFree(p);
+    if (h_prog) cudaFreeHost(h_prog);
     if (h_state) cudaFreeHost(h_state);
     if (h_red) cudaFreeHost(h_red);
     if (h_flags) cudaFreeHost(h_flags);
@@ -354,6 +357,9 @@ struct Solver : rba_handle {
     TRY(dalloc(&d_epart, (size_t)EBLOCKS * 6)); TRY(dalloc(&d_red, 8)); TRY(dalloc(&d_flags, 4));
     TRY(dalloc(&d_cam_cnt, (size_t)nc));
     TRY(dalloc(&d_state, 1));
+    CU(cudaHostAlloc((void**)&h_prog, 64, cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void**)&d_prog, h_prog, 0));
+    h_prog[0] = 0; h_prog[1] = 0;
     CU(cudaMallocHost((void**)&h_state, 2 * sizeof(PcgState)));
     CU(cudaMallocHost((void**)&h_red, 24 * sizeof(double)));
     CU(cudaMallocHost((void**)&h_flags, 12 * sizeof(int)));
@@ -782,7 +788,7 @@ struct Solver : rba_handle {
     PeerComm c = pc;
     if (!fused_ar) c.nranks = 1;
     return launch_ex(k_pcg_vec<S>, pcg_cluster, VEC_THREADS, 0, pdl && use_pdl, pcg_cluster, D, d_state, lambda, i, mode, (double)opt.eta,
-                     (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl), c, ar_seq, from_partials ? op_item_ptr : (const int*)nullptr);
+                     (int)opt.min_linear_solver_iterations, is_last, (int)(pdl && use_pdl), c, ar_seq, from_partials ? op_item_ptr : (const int*)nullptr, d_prog);
   }
   // finish one operator application inside PCG (H v for v = p in mode 0/1, x in mode 2) and do the vector step
   int pcg_apply(int i, int mode, int is_last, S lambda) {
@@ -892,35 +898,56 @@ struct Solver : rba_handle {
     CU(cudaMemsetAsync(d_state, 0, sizeof(PcgState), stream));
     const int max_it = std::max(opt.max_linear_solver_iterations, 1);
     const int period = opt.residual_reset_period;
-    const int chk = opt.pcg_check_period;
+    // The vector kernel publishes the number of the last completed iteration and the end of the solve in host-mapped pinned
+    // memory (h_prog); the host enqueues at most pcg_check_period iterations beyond that and stops as soon as it sees the
+    // end: no copy or event between the kernels of the loop, and at most pcg_check_period no-op iterations after the end
+    // (one GPU, and the peer-memory exchange, whose no-op kernels leave before they communicate).
+    const int depth = opt.pcg_check_period;
+    h_prog[0] = 0; h_prog[1] = 0;  // nothing in flight writes them: the stream has been synchronised since the previous solve
+    // The ranks stop enqueueing at slightly different iterations (whenever each sees the end), so the sequence numbers of the
+    // operator exchange restart from a per-solve base that every rank computes alike
+    ar_seq = (++pcg_solve_id) * (2 * max_it + 4);
     rc = pcg_vec(0, 3, false, 0, lambda); if (rc) return rc;  // x = 0, r = b, z = M^-1 r, rho, p = z
-    int i = 1;
-    int pending[2] = {0, 0};
-    int slot = 0;
-    bool finished = false;
-    while (i <= max_it && !finished) {
-      const int chunk_end = std::min(i + chk - 1, max_it);
-      for (; i <= chunk_end; ++i) {
-        const int is_last = (i == max_it) ? 1 : 0;
-        matvec_kernels(D.p, &d_state->done, true);
-        if (i % period == 0) {
-          rc = pcg_apply(i, 1, 0, lambda); if (rc) return rc;
-          matvec_kernels(D.x, &d_state->done, true);
-          rc = pcg_apply(i, 2, is_last, lambda); if (rc) return rc;
-        } else {
-          rc = pcg_apply(i, 0, is_last, lambda); if (rc) return rc;
+    auto enqueue_iteration = [&](int i) -> int {
+      const int is_last = (i == max_it) ? 1 : 0;
+      matvec_kernels(D.p, &d_state->done, true);
+      if (i % period == 0) {
+        int r2 = pcg_apply(i, 1, 0, lambda); if (r2) return r2;
+        matvec_kernels(D.x, &d_state->done, true);
+        return pcg_apply(i, 2, is_last, lambda);
+      }
+      return pcg_apply(i, 0, is_last, lambda);
+    };
+    if (opt.nranks > 1 && !peer_ok) {
+      // NCCL exchange: every rank must enqueue the SAME number of all-reduces, so the decision to stop may depend only on
+      // the iteration count -- the flag is polled once per chunk of `depth` iterations, one chunk behind
+      int i = 1, pending[2] = {0, 0}, slot = 0;
+      bool finished = false;
+      while (i <= max_it && !finished) {
+        const int chunk_end = std::min(i + depth - 1, max_it);
+        for (; i <= chunk_end; ++i) { rc = enqueue_iteration(i); if (rc) return rc; }
+        CU(cudaMemcpyAsync(&h_state[slot], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(poll_ev[slot], stream));
+        pending[slot] = 1;
+        const int other = slot ^ 1;
+        if (pending[other]) {
+          CU(cudaEventSynchronize(poll_ev[other]));
+          pending[other] = 0;
+          if (h_state[other].done) finished = true;
         }
+        slot = other;
       }
-      CU(cudaMemcpyAsync(&h_state[slot], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
-      CU(cudaEventRecord(poll_ev[slot], stream));
-      pending[slot] = 1;
-      const int other = slot ^ 1;
-      if (pending[other]) {
-        CU(cudaEventSynchronize(poll_ev[other]));
-        pending[other] = 0;
-        if (h_state[other].done) finished = true;
+    } else {
+      volatile int* prog = h_prog;
+      for (int i = 1; i <= max_it; ++i) {
+        unsigned spins = 0;
+        while (!prog[1] && i - prog[0] > depth) {
+          // every 64k polls: has the stream run dry (a launch failed, or the kernels ended without publishing)?  Then do not wait.
+          if ((++spins & 0xffffu) == 0 && cudaStreamQuery(stream) != cudaErrorNotReady) break;
+        }
+        if (prog[1]) break;
+        rc = enqueue_iteration(i); if (rc) return rc;
       }
-      slot = other;
     }
     CU(cudaMemcpyAsync(&h_state[0], d_state, sizeof(PcgState), cudaMemcpyDeviceToHost, stream));
     if (inc_out) CU(cudaMemcpyAsync(inc_out, D.inc, (size_t)9 * nc * sizeof(S), cudaMemcpyDeviceToHost, stream));
