@@ -49,6 +49,21 @@ def test_default_opts_match_reference_defaults():
     assert o.residual_reset_period == 10 and o.nranks == 1
 
 
+def test_default_lm_opts_match_reference_defaults():
+    """rba_lm_run's schedule parameters default to SolverOptions' (bal/solver_options.hpp: trust region 1e4 in [1e-32, 1e16],
+    vee 2 x 2, function tolerance 1e-6, 20 iterations, optimized_cost ERROR)"""
+    o = _lib.LmOpts()
+    _lib.lib().rba_default_lm_opts(C.byref(o))
+    assert (o.initial_trust_region_radius, o.min_trust_region_radius, o.max_trust_region_radius) == (1e4, 1e-32, 1e16)
+    assert (o.min_relative_decrease, o.initial_vee, o.vee_factor, o.function_tolerance) == (0.0, 2.0, 2.0, 1e-6)
+    assert (o.max_num_iterations, o.optimized_cost) == (20, 0)
+    # the Python mirror of the options carries the same defaults
+    import rootba_b200 as rb
+    so = rb.SolverOptions()
+    assert (so.initial_trust_region_radius, so.min_trust_region_radius, so.max_trust_region_radius) == (1e4, 1e-32, 1e16)
+    assert (so.initial_vee, so.vee_factor, so.function_tolerance, so.max_num_iterations) == (2.0, 2.0, 1e-6, 20)
+
+
 @pytest.mark.parametrize("shape", [(12, 300, 4.1, 400), (150, 1500, 9.0, 150), (300, 120, 60.0, 300), (9, 77, 2.0001, 400)])
 def test_layout_selftest(shape):
     """indexing is bit-exact: every observation lands in exactly one slot with its camera, row chunks tile every panel
@@ -85,11 +100,12 @@ def test_layout_rejects_unsorted_and_short_tracks(tiny_problem):
 
 def test_header_is_plain_c_and_links(tmp_path):
     """the drop-in boundary is a C ABI: the header must compile as C99 (no C++ types), a C program must link and run
-    against the library without a GPU, and the ctypes mirrors of the six structs must have the C sizes"""
+    against the library without a GPU, and the ctypes mirrors of the structs must have the C sizes"""
     import subprocess
     from conftest import ROOT
     structs = {"rba_problem_view": _lib.ProblemView, "rba_solver_opts": _lib.SolverOpts, "rba_residual_info": _lib.ResidualInfo,
-               "rba_cg_summary": _lib.CgSummary, "rba_stage_timings": _lib.StageTimings, "rba_workload_stats": _lib.WorkloadStats}
+               "rba_cg_summary": _lib.CgSummary, "rba_stage_timings": _lib.StageTimings, "rba_workload_stats": _lib.WorkloadStats,
+               "rba_lm_step_result": _lib.LmStepResult, "rba_lm_opts": _lib.LmOpts, "rba_lm_iteration": _lib.LmIteration}
     src = tmp_path / "abi.c"
     src.write_text(
         '#include "rootba_b200.h"\n#include <stdio.h>\n'
