@@ -113,3 +113,65 @@ def test_first_order_model_predicts_the_true_cost_change(dense_case):
     e1 = o.compute_error()["all"]["error"]
     assert l_diff > 0 and e0 > e1
     assert (e0 - e1) / l_diff == pytest.approx(1.0, abs=5e-2)
+
+
+def test_sc_and_power_sc_linearizors_match_dense_normal_equations(dense_case):
+    """the Schur-complement and Power-SC restatements (the checkers of tests/test_gpu_sc.py; reference
+    solver/linearizor_sc.cpp, solver/linearizor_power_sc.cpp, sc/linearization_power_sc.hpp:92-160) against the same dense
+    derivation:  H = Hpp + lambda I - E0,  Hpp = Jp_s^T Jp_s (block diagonal),  E0 = W M^-1 W^T,
+    power series  x_m = sum_{i=0..m} ((Hpp + lambda I)^-1 E0)^i (Hpp + lambda I)^-1 (-b)  ->  -H^-1 b"""
+    prob, (Jp, Jl, r) = dense_case
+    lam = 1e-3
+    eps = float(np.sqrt(1e-10))
+    D, sl, Jps, Jls, Minv, H, b = _reduced(Jp, Jl, r, lam, prob.nl, eps)
+    N = H.shape[0]
+    W = Jps.T @ Jls
+    E0 = W @ Minv @ W.T
+    Hpp_inv = np.linalg.inv(Jps.T @ Jps + lam * np.eye(N))  # block diagonal: one 9x9 block per camera
+    opts = orc.default_options(eta=1e-15, max_linear_solver_iterations=4000, num_threads=1)
+    o = orc.Oracle(prob, np.float64, opts)
+    o.compute_error()
+    o.scl_linearize()
+    assert rel_err(o.scl_get_scaling(), D) < 1e-13
+    x = np.random.default_rng(2).uniform(-1, 1, N)
+    # Schur-complement solver: same b, same block-Jacobi preconditioner, same solution as the dense system
+    inc, dbg = o.scl_solve(lam)
+    assert rel_err(dbg["b"], b) < 1e-11
+    for c in range(prob.nc):
+        assert rel_err(dbg["inv_blocks"][c], np.linalg.inv(H[9 * c:9 * c + 9, 9 * c:9 * c + 9])) < 1e-8, c
+    want_inc = -np.linalg.solve(H, b)
+    assert rel_err(inc, want_inc) < 1e-8 * np.linalg.cond(H) ** 0.5
+    # E0 alone (the operator of the power series)
+    assert rel_err(o.scl_e0(lam, x), E0 @ x) < 1e-11
+    # truncated power series, term by term
+    term = Hpp_inv @ (-b)
+    acc = term.copy()
+    partial = {0: acc.copy()}
+    for i in range(1, 41):
+        term = Hpp_inv @ (E0 @ term)
+        acc = acc + term
+        partial[i] = acc.copy()
+    for m in (0, 1, 5, 40):
+        inc_m, d = o.scl_power_solve(lam, power_order=m, q_tolerance=0.0)
+        assert rel_err(d["b"], b) < 1e-11
+        assert rel_err(inc_m, partial[m]) < 1e-10, m
+    # the series converges towards the exact solution (spectral radius of Hpp^-1 E0 < 1), monotonically in the H-norm
+    errs = [np.sqrt((partial[m] - want_inc) @ H @ (partial[m] - want_inc)) for m in (0, 5, 40)]
+    assert errs[0] > errs[1] > errs[2]
+    # the reference's stopping rule  zeta = i |term_i| / |sum| < q_tolerance  (linearization_power_sc.hpp:147-156)
+    inc_q, dq = o.scl_power_solve(lam, power_order=40, q_tolerance=0.1)
+    term = Hpp_inv @ (-b); acc = term.copy(); stop = 40
+    for i in range(1, 41):
+        term = Hpp_inv @ (E0 @ term); acc = acc + term
+        if i * np.linalg.norm(term) / np.linalg.norm(acc) < 0.1:
+            stop = i
+            break
+    assert dq["power_order"] == stop and dq["termination"] == (1 if stop < 40 else 0)
+    assert rel_err(inc_q, acc) < 1e-10
+    # back substitution of the SC linearizor: model decrease and landmark update as in the dense derivation
+    inc, _ = o.scl_solve(lam)
+    dl_s = -Minv @ (Jls.T @ r + Jls.T @ (Jps @ inc))
+    want_l = 0.5 * r @ r - 0.5 * np.sum((r + Jps @ inc + Jls @ dl_s) ** 2)
+    assert o.scl_apply(inc) == pytest.approx(want_l, rel=1e-9)
+    _, lms_new = o.get_state()
+    assert rel_err(lms_new, prob.lms + (sl * dl_s).reshape(-1, 3)) < 1e-12
