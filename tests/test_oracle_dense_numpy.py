@@ -119,7 +119,10 @@ def test_sc_and_power_sc_linearizors_match_dense_normal_equations(dense_case):
     """the Schur-complement and Power-SC restatements (the checkers of tests/test_gpu_sc.py; reference
     solver/linearizor_sc.cpp, solver/linearizor_power_sc.cpp, sc/linearization_power_sc.hpp:92-160) against the same dense
     derivation:  H = Hpp + lambda I - E0,  Hpp = Jp_s^T Jp_s (block diagonal),  E0 = W M^-1 W^T,
-    power series  x_m = sum_{i=0..m} ((Hpp + lambda I)^-1 E0)^i (Hpp + lambda I)^-1 (-b)  ->  -H^-1 b"""
+    power series  x_m = sum_{i=0..m} ((Hpp + lambda I)^-1 E0)^i (Hpp + lambda I)^-1 (-b)  ->  -H^-1 b
+    These are the properties the reference's own tests check between its classes -- sc/linearization_power_sc.test.cpp:67-137
+    (Hpp^-1 == inverted JACOBI blocks), :142-211 (b and the product of PowerSC == explicit SC), :214-300 (solve for m = 0 and
+    m = 5 == the series written out), cg/preconditioner.test.cpp:59-136 -- here against dense numpy instead of against each other."""
     prob, (Jp, Jl, r) = dense_case
     lam = 1e-3
     eps = float(np.sqrt(1e-10))
