@@ -792,7 +792,11 @@ struct Solver : rba_handle {
   }
   // finish one operator application inside PCG (H v for v = p in mode 0/1, x in mode 2) and do the vector step
   int pcg_apply(int i, int mode, int is_last, S lambda) {
-    if (opt.nranks == 1 && pcg_partials) {
+    // The hand-over through per-segment sums is taken when a cluster CTA's share of the cameras fits the vector kernel's
+    // register-resident layout (<= 1820 cameras with a 16-CTA cluster); larger camera counts on one GPU (Final-13682)
+    // keep the arrival-counter reduction below, the combination that was measured at that size.
+    const bool vec_cached = 9 * ((nc + pcg_cluster - 1) / pcg_cluster) <= VEC_THREADS * VEC_EPT;
+    if (opt.nranks == 1 && pcg_partials && vec_cached) {
       // one GPU: the vector kernel adds the per-segment sums itself (same order as k_cam_reduce_final's last arriver:
       // bit-identical) -- no arrival counters, fences or second pass in the reduction
       int rc = launch_ex(k_cam_reduce<S>, grid_for(n_op_items, 8, 8), 256, 0, use_pdl, 1, (const S*)D.yobs, op_slots, op_items, n_op_items, D.partial,
